@@ -1,0 +1,498 @@
+"""ctypes binding of libfredholm_b200.so (C ABI: include/fredholm_b200.h).
+
+Mirrors the reference's call sequence (fredholm::Renderer, renderer.h:29-846):
+    r = Renderer(device); r.set_resolution(w, h); r.load_scene(path) / r.set_scene(arrays)
+    r.build_accel(); r.render(camera, bg, layers, n_samples, max_depth); r.wait()
+There is no CPU path: every call goes to the CUDA library and raises if it is missing.
+"""
+import ctypes as C
+import os
+from dataclasses import dataclass
+
+import numpy as np
+
+from .types import MATERIAL_DTYPE, SceneArrays
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfredholm_b200.so")
+
+
+class LibraryNotBuilt(RuntimeError):
+    pass
+
+
+class FredholmError(RuntimeError):
+    pass
+
+
+class _Layers(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("beauty", "position", "depth", "normal", "texcoord", "albedo")]
+
+
+class _PostProcessParams(C.Structure):
+    _fields_ = [("use_bloom", C.c_int), ("bloom_threshold", C.c_float), ("bloom_sigma", C.c_float),
+                ("ISO", C.c_float), ("chromatic_aberration", C.c_float)]
+
+
+_fp = C.POINTER(C.c_float)
+_up = C.POINTER(C.c_uint32)
+_u8p = C.POINTER(C.c_uint8)
+_u64p = C.POINTER(C.c_uint64)
+_vp = C.c_void_p
+
+# name -> (restype, argtypes); this table is also what the "exports every symbol" test walks
+SIGNATURES = {
+    "fr_last_error": (C.c_char_p, []),
+    "fr_device_count": (C.c_int, []),
+    "fr_version": (C.c_char_p, []),
+    "fr_renderer_create": (_vp, [C.c_int]),
+    "fr_renderer_destroy": (None, [_vp]),
+    "fr_load_scene": (C.c_int, [_vp, C.c_char_p, C.c_int]),
+    "fr_stage_texture": (C.c_int, [_vp, _u8p, C.c_uint32, C.c_uint32, C.c_int]),
+    "fr_set_scene_arrays": (C.c_int, [_vp, _fp, _fp, _fp, C.c_uint32, _up, _up, _up, C.c_uint32, _vp, C.c_uint32,
+                                      _up, _up, _fp, C.c_uint32]),
+    "fr_get_scene_sizes": (C.c_int, [_vp, _up]),
+    "fr_get_scene_arrays": (C.c_int, [_vp, _fp, _fp, _fp, _up, _up, _up, _vp, _up, _up, _fp, _fp]),
+    "fr_get_texture_info": (C.c_int, [_vp, C.c_uint32, _up, _up, _up]),
+    "fr_get_texture_data": (C.c_int, [_vp, C.c_uint32, _u8p]),
+    "fr_scene_create": (_vp, []),
+    "fr_scene_destroy": (None, [_vp]),
+    "fr_scene_load": (C.c_int, [_vp, C.c_char_p, C.c_int]),
+    "fr_scene_get_sizes": (C.c_int, [_vp, _up]),
+    "fr_scene_get_arrays": (C.c_int, [_vp, _fp, _fp, _fp, _up, _up, _up, _vp, _up, _up, _fp, _fp]),
+    "fr_scene_get_texture_info": (C.c_int, [_vp, C.c_uint32, _up, _up, _up]),
+    "fr_scene_get_texture_data": (C.c_int, [_vp, C.c_uint32, _u8p]),
+    "fr_scene_update_animation": (C.c_int, [_vp, C.c_float]),
+    "fr_set_scene": (C.c_int, [_vp, _vp]),
+    "fr_build_accel": (C.c_int, [_vp]),
+    "fr_get_accel_info": (C.c_int, [_vp, _up, _fp, _u64p]),
+    "fr_set_time": (C.c_int, [_vp, C.c_float]),
+    "fr_set_transforms": (C.c_int, [_vp, _fp, C.c_uint32]),
+    "fr_set_directional_light": (C.c_int, [_vp, _fp, _fp, C.c_float]),
+    "fr_clear_directional_light": (C.c_int, [_vp]),
+    "fr_set_sky_intensity": (C.c_int, [_vp, C.c_float]),
+    "fr_load_arhosek_sky": (C.c_int, [_vp, C.c_float, C.c_float]),
+    "fr_clear_arhosek_sky": (C.c_int, [_vp]),
+    "fr_set_ibl": (C.c_int, [_vp, _fp, C.c_uint32, C.c_uint32]),
+    "fr_load_ibl": (C.c_int, [_vp, C.c_char_p]),
+    "fr_clear_ibl": (C.c_int, [_vp]),
+    "fr_set_resolution": (C.c_int, [_vp, C.c_uint32, C.c_uint32]),
+    "fr_init_render_states": (C.c_int, [_vp]),
+    "fr_set_sample_offset": (C.c_int, [_vp, C.c_uint32]),
+    "fr_get_sample_count": (C.c_uint32, [_vp]),
+    "fr_set_film_mode": (C.c_int, [_vp, C.c_int]),
+    "fr_set_max_wave_paths": (C.c_int, [_vp, C.c_uint64]),
+    "fr_render": (C.c_int, [_vp, _fp, C.c_float, C.c_float, C.c_float, _fp, C.POINTER(_Layers), C.c_uint32,
+                            C.c_uint32]),
+    "fr_wait": (C.c_int, [_vp]),
+    "fr_render_frame_host": (C.c_int, [_vp, _fp, C.c_float, C.c_float, C.c_float, _fp, C.POINTER(_Layers),
+                                       C.c_uint32, C.c_uint32]),
+    "fr_scale_layers": (C.c_int, [_vp, C.POINTER(_Layers), C.c_float]),
+    "fr_get_statistics": (C.c_int, [_vp, _u64p]),
+    "fr_reset_statistics": (C.c_int, [_vp]),
+    "fr_get_stream": (C.c_uint64, [_vp]),
+    "fr_post_process": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.POINTER(_PostProcessParams), _vp]),
+    "fr_tone_mapping": (C.c_int, [_vp, C.c_int, C.c_int, C.c_float, C.c_float, _vp]),
+    "fr_device_alloc": (_vp, [C.c_size_t]),
+    "fr_device_free": (C.c_int, [_vp]),
+    "fr_device_memset": (C.c_int, [_vp, C.c_int, C.c_size_t]),
+    "fr_copy_to_device": (C.c_int, [_vp, _vp, C.c_size_t]),
+    "fr_copy_to_host": (C.c_int, [_vp, _vp, C.c_size_t]),
+    "fr_device_synchronize": (C.c_int, []),
+    "fr_trace_closest": (C.c_int, [_vp, _fp, C.c_uint32, C.c_float, C.c_float, _up, _fp, _u64p]),
+    "fr_primary_rays": (C.c_int, [_vp, _fp, C.c_float, C.c_float, C.c_float, C.c_uint32, _fp]),
+    "fr_sampler_sequence": (C.c_int, [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_char_p, _fp]),
+    "fr_bsdf_eval_sample": (C.c_int, [_fp, C.c_uint32, _fp]),
+    "fr_sky_radiance": (C.c_int, [_vp, _fp, C.c_uint32, _fp]),
+    "fr_arhosek_cook": (C.c_int, [C.c_float, C.c_float, C.c_float, _fp]),
+    "fr_camera_transform": (C.c_int, [_fp, _fp]),
+    "fr_camera_walk": (C.c_int, [_fp, C.c_float, C.c_float, C.c_int, C.c_float, _fp]),
+}
+
+_lib = None
+
+
+def lib():
+    """Loads libfredholm_b200.so (once).  Raises LibraryNotBuilt if it is missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise LibraryNotBuilt(
+                "%s not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(there is no CPU fallback)" % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise FredholmError(lib().fr_last_error().decode("utf-8", "replace"))
+
+
+def _f(a):
+    return a.ctypes.data_as(_fp)
+
+
+def _u(a):
+    return a.ctypes.data_as(_up)
+
+
+def _f32(x, n=None):
+    a = np.ascontiguousarray(x, dtype=np.float32).reshape(-1)
+    if n is not None:
+        assert a.size == n, (a.size, n)
+    return a
+
+
+@dataclass
+class Camera:
+    """Camera parameter block handed to render(): camera-to-world 3x4 rows + thin lens
+    (reference CameraParams, shared.h:59-64).  `from_origin` mirrors fredholm::Camera's
+    constructor (camera.h:51-69): look down -z from `origin`."""
+    transform: np.ndarray   # (12,) f32 row-major 3x4 camera-to-world
+    fov: float = 0.5 * np.pi
+    F: float = 8.0
+    focus: float = 10000.0
+
+    @staticmethod
+    def from_origin(origin, fov=0.5 * np.pi, F=8.0, focus=10000.0):
+        out = np.zeros(12, dtype=np.float32)
+        _check(lib().fr_camera_transform(_f(_f32(origin, 3)), _f(out)))
+        return Camera(out, float(fov), float(F), float(focus))
+
+
+LAYER_NAMES = ("beauty", "position", "depth", "normal", "texcoord", "albedo")
+
+
+class DeviceLayers:
+    """Caller-owned device AOV buffers (reference: the app owns six CUDABuffers,
+    controller.cpp:80-124)."""
+
+    def __init__(self, width, height, names=LAYER_NAMES):
+        self.width, self.height = width, height
+        self.ptr = {}
+        self.names = tuple(names)
+        n = width * height
+        for name in self.names:
+            nbytes = n * (4 if name == "depth" else 16)
+            p = lib().fr_device_alloc(nbytes)
+            if not p:
+                raise FredholmError(lib().fr_last_error().decode())
+            self.ptr[name] = p
+        self.clear()
+
+    def clear(self):
+        n = self.width * self.height
+        for name, p in self.ptr.items():
+            _check(lib().fr_device_memset(p, 0, n * (4 if name == "depth" else 16)))
+
+    def struct(self):
+        s = _Layers()
+        for name in LAYER_NAMES:
+            setattr(s, name, self.ptr.get(name))
+        return s
+
+    def download(self, name):
+        n = self.width * self.height
+        c = 1 if name == "depth" else 4
+        out = np.empty((self.height, self.width, c) if c == 4 else (self.height, self.width), dtype=np.float32)
+        _check(lib().fr_copy_to_host(out.ctypes.data_as(_vp), self.ptr[name], n * 4 * c))
+        return out
+
+    def free(self):
+        for p in self.ptr.values():
+            lib().fr_device_free(p)
+        self.ptr = {}
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def _read_scene(handle, sizes_fn, arrays_fn, texinfo_fn, texdata_fn) -> SceneArrays:
+    sz = np.zeros(6, dtype=np.uint32)
+    _check(sizes_fn(handle, _u(sz)))
+    nv, nf, nm, nt, ns, _ = [int(v) for v in sz]
+    v = np.zeros((nv, 3), np.float32)
+    n = np.zeros((nv, 3), np.float32)
+    t = np.zeros((nv, 2), np.float32)
+    idx = np.zeros((nf, 3), np.uint32)
+    mid = np.zeros(nf, np.uint32)
+    iid = np.zeros(nf, np.uint32)
+    mats = np.zeros(nm, MATERIAL_DTYPE)
+    so = np.zeros(ns, np.uint32)
+    sn = np.zeros(ns, np.uint32)
+    tr = np.zeros((ns, 16), np.float32)
+    cam = np.zeros(16, np.float32)
+    _check(arrays_fn(handle, _f(v), _f(n), _f(t), _u(idx), _u(mid), _u(iid), mats.ctypes.data_as(_vp), _u(so),
+                     _u(sn), _f(tr), _f(cam)))
+    textures = []
+    for i in range(nt):
+        w, h, c = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        _check(texinfo_fn(handle, i, C.byref(w), C.byref(h), C.byref(c)))
+        img = np.zeros((h.value, w.value, 4), np.uint8)
+        _check(texdata_fn(handle, i, img.ctypes.data_as(_u8p)))
+        textures.append((img, bool(c.value)))
+    s = SceneArrays(v, n, t, idx, mid, mats, so, sn, iid, tr, textures)
+    s.has_camera = bool(sz[5])
+    s.camera_transform = cam
+    return s
+
+
+class Scene:
+    """Host-side fredholm::Scene (file loaders, animation); needs no GPU."""
+
+    def __init__(self):
+        self._h = lib().fr_scene_create()
+
+    def load_model(self, path, clear=True):
+        _check(lib().fr_scene_load(self._h, os.fsencode(str(path)), 1 if clear else 0))
+
+    def arrays(self) -> SceneArrays:
+        L = lib()
+        return _read_scene(self._h, L.fr_scene_get_sizes, L.fr_scene_get_arrays, L.fr_scene_get_texture_info,
+                           L.fr_scene_get_texture_data)
+
+    def update_animation(self, t):
+        _check(lib().fr_scene_update_animation(self._h, float(t)))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().fr_scene_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Renderer:
+    def __init__(self, device=0):
+        L = lib()
+        if L.fr_device_count() <= device:
+            raise FredholmError("no CUDA device %d (fredholm_b200 has no CPU fallback)" % device)
+        self._h = L.fr_renderer_create(device)
+        if not self._h:
+            raise FredholmError(L.fr_last_error().decode())
+        self.width = self.height = 0
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().fr_renderer_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- scene ----
+    def load_scene(self, path, clear=True):
+        _check(lib().fr_load_scene(self._h, os.fsencode(str(path)), 1 if clear else 0))
+
+    def set_scene(self, s: SceneArrays):
+        L = lib()
+        for rgba8, is_color in s.textures:
+            img = np.ascontiguousarray(rgba8, dtype=np.uint8)
+            assert img.ndim == 3 and img.shape[2] == 4
+            if L.fr_stage_texture(self._h, img.ctypes.data_as(_u8p), img.shape[1], img.shape[0],
+                                  1 if is_color else 0) < 0:
+                raise FredholmError(L.fr_last_error().decode())
+        _check(L.fr_set_scene_arrays(
+            self._h, _f(s.vertices), _f(s.normals), _f(s.texcoords), len(s.vertices), _u(s.indices),
+            _u(s.material_ids), _u(s.instance_ids), len(s.indices), s.materials.ctypes.data_as(_vp),
+            len(s.materials), _u(s.submesh_offsets), _u(s.submesh_n_faces), _f(s.transforms),
+            len(s.submesh_offsets)))
+
+    def get_scene(self) -> SceneArrays:
+        L = lib()
+        return _read_scene(self._h, L.fr_get_scene_sizes, L.fr_get_scene_arrays, L.fr_get_texture_info,
+                           L.fr_get_texture_data)
+
+    def set_scene_object(self, scene: "Scene"):
+        _check(lib().fr_set_scene(self._h, scene._h))
+
+    def build_accel(self):
+        _check(lib().fr_build_accel(self._h))
+
+    def accel_info(self):
+        out = np.zeros(3, np.uint32)
+        ms = C.c_float()
+        nbytes = C.c_uint64()
+        _check(lib().fr_get_accel_info(self._h, _u(out), C.byref(ms), C.byref(nbytes)))
+        return dict(n_faces=int(out[0]), n_nodes=int(out[1]), depth=int(out[2]), build_ms=ms.value,
+                    bytes=int(nbytes.value))
+
+    def set_time(self, t):
+        _check(lib().fr_set_time(self._h, float(t)))
+
+    def set_transforms(self, transforms):
+        tr = _f32(transforms).reshape(-1, 16)
+        _check(lib().fr_set_transforms(self._h, _f(tr), len(tr)))
+
+    # ---- lights / sky ----
+    def set_directional_light(self, le, direction, angle):
+        _check(lib().fr_set_directional_light(self._h, _f(_f32(le, 3)), _f(_f32(direction, 3)), float(angle)))
+
+    def clear_directional_light(self):
+        _check(lib().fr_clear_directional_light(self._h))
+
+    def set_sky_intensity(self, v):
+        _check(lib().fr_set_sky_intensity(self._h, float(v)))
+
+    def load_arhosek_sky(self, turbidity, albedo):
+        _check(lib().fr_load_arhosek_sky(self._h, float(turbidity), float(albedo)))
+
+    def clear_arhosek_sky(self):
+        _check(lib().fr_clear_arhosek_sky(self._h))
+
+    def set_ibl(self, rgba32f):
+        img = np.ascontiguousarray(rgba32f, dtype=np.float32)
+        assert img.ndim == 3 and img.shape[2] == 4
+        _check(lib().fr_set_ibl(self._h, _f(img), img.shape[1], img.shape[0]))
+
+    def clear_ibl(self):
+        _check(lib().fr_clear_ibl(self._h))
+
+    # ---- film ----
+    def set_resolution(self, width, height):
+        self.width, self.height = int(width), int(height)
+        _check(lib().fr_set_resolution(self._h, self.width, self.height))
+
+    def init_render_states(self):
+        _check(lib().fr_init_render_states(self._h))
+
+    def set_sample_offset(self, first):
+        _check(lib().fr_set_sample_offset(self._h, int(first)))
+
+    def sample_count(self):
+        return int(lib().fr_get_sample_count(self._h))
+
+    def set_film_mode(self, mode):
+        _check(lib().fr_set_film_mode(self._h, {"mean": 0, "sum": 1}.get(mode, mode)))
+
+    def set_max_wave_paths(self, n):
+        _check(lib().fr_set_max_wave_paths(self._h, int(n)))
+
+    # ---- render ----
+    def render(self, camera: Camera, bg_color, layers, n_samples, max_depth):
+        """layers: DeviceLayers, or a dict name -> device pointer (e.g. torch tensor .data_ptr())."""
+        if isinstance(layers, DeviceLayers):
+            st = layers.struct()
+        else:
+            st = _Layers()
+            for name in LAYER_NAMES:
+                setattr(st, name, layers.get(name))
+        _check(lib().fr_render(self._h, _f(_f32(camera.transform, 12)), camera.fov, camera.F, camera.focus,
+                               _f(_f32(bg_color, 3)), C.byref(st), int(n_samples), int(max_depth)))
+
+    def wait(self):
+        _check(lib().fr_wait(self._h))
+
+    def render_frame_host(self, camera: Camera, bg_color, n_samples, max_depth, names=("beauty",), out=None):
+        """One frame through host buffers (clear, render, read back).  Returns dict of arrays."""
+        n = self.width * self.height
+        res = out if out is not None else {}
+        st = _Layers()
+        for name in names:
+            if name not in res:
+                res[name] = np.empty((self.height, self.width, 4) if name != "depth" else (self.height, self.width),
+                                     dtype=np.float32)
+            assert res[name].size == n * (1 if name == "depth" else 4)
+            setattr(st, name, res[name].ctypes.data_as(_vp))
+        _check(lib().fr_render_frame_host(self._h, _f(_f32(camera.transform, 12)), camera.fov, camera.F,
+                                          camera.focus, _f(_f32(bg_color, 3)), C.byref(st), int(n_samples),
+                                          int(max_depth)))
+        return res
+
+    def scale_layers(self, layers, scale):
+        st = layers.struct() if isinstance(layers, DeviceLayers) else None
+        if st is None:
+            st = _Layers()
+            for name in LAYER_NAMES:
+                setattr(st, name, layers.get(name))
+        _check(lib().fr_scale_layers(self._h, C.byref(st), float(scale)))
+
+    def statistics(self):
+        out = np.zeros(5, np.uint64)
+        _check(lib().fr_get_statistics(self._h, out.ctypes.data_as(_u64p)))
+        d = dict(paths=int(out[0]), rays_radiance=int(out[1]), rays_shadow=int(out[2]), rays_light=int(out[3]),
+                 kernel_launches=int(out[4]))
+        d["rays"] = d["rays_radiance"] + d["rays_shadow"] + d["rays_light"]
+        return d
+
+    def reset_statistics(self):
+        _check(lib().fr_reset_statistics(self._h))
+
+    def stream(self):
+        return int(lib().fr_get_stream(self._h))
+
+    # ---- stage-level queries (parity tests) ----
+    def trace_closest(self, rays, tmin=0.0, tmax=1e9, counters=False):
+        rays = np.ascontiguousarray(rays, dtype=np.float32).reshape(-1, 6)
+        n = len(rays)
+        ids = np.zeros((n, 2), np.uint32)
+        tuv = np.zeros((n, 3), np.float32)
+        cnt = np.zeros(2, np.uint64)
+        _check(lib().fr_trace_closest(self._h, _f(rays), n, float(tmin), float(tmax), _u(ids), _f(tuv),
+                                      cnt.ctypes.data_as(_u64p) if counters else None))
+        return (ids, tuv, cnt) if counters else (ids, tuv)
+
+    def primary_rays(self, camera: Camera, n_spp=0):
+        out = np.zeros((self.height, self.width, 6), np.float32)
+        _check(lib().fr_primary_rays(self._h, _f(_f32(camera.transform, 12)), camera.fov, camera.F, camera.focus,
+                                     int(n_spp), _f(out)))
+        return out
+
+    def sky_radiance(self, dirs):
+        d = np.ascontiguousarray(dirs, dtype=np.float32).reshape(-1, 3)
+        out = np.zeros_like(d)
+        _check(lib().fr_sky_radiance(self._h, _f(d), len(d), _f(out)))
+        return out
+
+
+def sampler_sequence(width, height, seed, image_idx, n_spp, kinds):
+    n_out = sum(1 if k == "1" else 2 for k in kinds)
+    out = np.zeros(n_out, np.float32)
+    _check(lib().fr_sampler_sequence(width, height, seed, image_idx, n_spp, kinds.encode(), _f(out)))
+    return out
+
+
+def bsdf_eval_sample(cases):
+    """cases: (n,40) f32 -> (n,11): eval f[3], pdf, sample wi[3], f[3], pdf."""
+    c = np.ascontiguousarray(cases, dtype=np.float32).reshape(-1, 40)
+    out = np.zeros((len(c), 11), np.float32)
+    _check(lib().fr_bsdf_eval_sample(_f(c), len(c), _f(out)))
+    return out
+
+
+def arhosek_cook(turbidity, albedo, elevation):
+    out = np.zeros(30, np.float32)
+    _check(lib().fr_arhosek_cook(float(turbidity), float(albedo), float(elevation), _f(out)))
+    return out
+
+
+def camera_walk(origin, d_phi, d_theta, movement, dt):
+    out = np.zeros(12, np.float32)
+    _check(lib().fr_camera_walk(_f(_f32(origin, 3)), float(d_phi), float(d_theta), int(movement), float(dt), _f(out)))
+    return out
+
+
+def post_process(beauty_in, high, temp, width, height, out, use_bloom=True, bloom_threshold=2.0, bloom_sigma=5.0,
+                 ISO=80.0, chromatic_aberration=1.0):
+    p = _PostProcessParams(1 if use_bloom else 0, bloom_threshold, bloom_sigma, ISO, chromatic_aberration)
+    _check(lib().fr_post_process(beauty_in, high, temp, width, height, C.byref(p), out))
+
+
+def tone_mapping(beauty_in, width, height, out, ISO=80.0, chromatic_aberration=1.0):
+    _check(lib().fr_tone_mapping(beauty_in, width, height, ISO, chromatic_aberration, out))

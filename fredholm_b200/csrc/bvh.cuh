@@ -1,0 +1,292 @@
+// Compressed 8-wide BVH (CWBVH, Ylitie/Karras/Laine 2017) and its traversal.
+//
+// Replaces the reference's OptiX acceleration structures + optixTrace
+// (renderer.h:434-552, pt.cu:82-123): B200 has no RT cores, so closest-hit /
+// any-hit queries are answered by this software traversal.
+//
+// Geometry is flattened to WORLD space at build time (instance i = submesh i with
+// transform i, renderer.h:509-527), so one single-level tree serves the whole
+// scene and a hit reports the global face index; (instance, primitive) are
+// recovered from the submesh table.
+//
+// The ray/triangle test is the watertight test of Woop, Benthin, Wald (2013).  Its
+// arithmetic is pinned instruction by instruction (explicit _rn intrinsics, no
+// compiler contraction) because primary-hit parity with the host oracle is
+// required to be bit-exact: see oracle/oracle_host.cpp (intersect_tri).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "vecmath.cuh"
+
+namespace frd
+{
+
+// 80-byte node, read as five 16-byte words.
+struct alignas(16) Node8 {
+  float px, py, pz;          // quantisation origin (node box lower corner)
+  uint8_t ex, ey, ez;        // biased exponents of the per-axis grid step
+  uint8_t imask;             // bit s set: slot s holds an internal child
+  uint32_t child_base;       // index of first internal child node
+  uint32_t tri_base;         // index of first leaf triangle
+  uint8_t meta[8];           // per slot: inner -> 0b001xxxxx (24+slot); leaf -> unary count<<5 | offset
+  uint8_t qlox[8], qloy[8];  // quantised child boxes
+  uint8_t qloz[8], qhix[8];
+  uint8_t qhiy[8], qhiz[8];
+};
+static_assert(sizeof(Node8) == 80, "CWBVH node must be 80 bytes");
+
+// 48-byte leaf triangle: world-space vertices; v0.w = global face index (bits),
+// v1.w = flags (bit 0: alpha-tested material, needs the any-hit path).
+struct alignas(16) LeafTri {
+  float4 v0, v1, v2;
+};
+
+struct BvhView {
+  const float4* nodes;  // Node8 as float4[5]
+  const float4* tris;   // LeafTri as float4[3]
+};
+
+struct HitRecord {
+  float t;        // hit distance (ray tmax if miss)
+  float u, v;     // barycentrics: p = (1-u-v) v0 + u v1 + v v2
+  uint32_t face;  // global face index, 0xffffffff = miss
+};
+
+constexpr uint32_t kNoHit = 0xffffffffu;
+
+// ---- watertight ray setup / test (must mirror oracle_host.cpp exactly) ---------
+struct RayShear {
+  float cx[3], cy[3], cz[3];
+};
+
+FR_D RayShear make_shear(const float3& d)
+{
+  const float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
+  int kz = 0;
+  float am = ax;
+  if (ay > am) {
+    kz = 1;
+    am = ay;
+  }
+  if (az > am) kz = 2;
+  int kx = kz == 2 ? 0 : kz + 1;
+  int ky = kx == 2 ? 0 : kx + 1;
+  const float dz = kz == 0 ? d.x : (kz == 1 ? d.y : d.z);
+  if (dz < 0.0f) {
+    const int t = kx;
+    kx = ky;
+    ky = t;
+  }
+  const float dx = kx == 0 ? d.x : (kx == 1 ? d.y : d.z);
+  const float dy = ky == 0 ? d.x : (ky == 1 ? d.y : d.z);
+  const float Sx = __fdiv_rn(dx, dz);
+  const float Sy = __fdiv_rn(dy, dz);
+  const float Sz = __fdiv_rn(1.0f, dz);
+  RayShear r;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    r.cx[i] = (i == kx) ? 1.0f : (i == kz) ? -Sx : 0.0f;
+    r.cy[i] = (i == ky) ? 1.0f : (i == kz) ? -Sy : 0.0f;
+    r.cz[i] = (i == kz) ? Sz : 0.0f;
+  }
+  return r;
+}
+
+FR_D float shear_dot(float ax, float ay, float az, const float c[3])
+{
+  return __fmaf_rn(az, c[2], __fmaf_rn(ay, c[1], __fmul_rn(ax, c[0])));
+}
+
+// true if tmin < t < tlim (or t == tlim when allow_equal), outputs t,u,v
+FR_D bool watertight_hit(const RayShear& s, const float3& o, const float4& v0, const float4& v1,
+                         const float4& v2, float tmin, float tlim, bool allow_equal, float& t,
+                         float& bu, float& bv)
+{
+  const float Ax0 = __fsub_rn(v0.x, o.x), Ay0 = __fsub_rn(v0.y, o.y), Az0 = __fsub_rn(v0.z, o.z);
+  const float Bx0 = __fsub_rn(v1.x, o.x), By0 = __fsub_rn(v1.y, o.y), Bz0 = __fsub_rn(v1.z, o.z);
+  const float Cx0 = __fsub_rn(v2.x, o.x), Cy0 = __fsub_rn(v2.y, o.y), Cz0 = __fsub_rn(v2.z, o.z);
+  const float Ax = shear_dot(Ax0, Ay0, Az0, s.cx), Ay = shear_dot(Ax0, Ay0, Az0, s.cy);
+  const float Bx = shear_dot(Bx0, By0, Bz0, s.cx), By = shear_dot(Bx0, By0, Bz0, s.cy);
+  const float Cx = shear_dot(Cx0, Cy0, Cz0, s.cx), Cy = shear_dot(Cx0, Cy0, Cz0, s.cy);
+  float U = __fsub_rn(__fmul_rn(Cx, By), __fmul_rn(Cy, Bx));
+  float V = __fsub_rn(__fmul_rn(Ax, Cy), __fmul_rn(Ay, Cx));
+  float W = __fsub_rn(__fmul_rn(Bx, Ay), __fmul_rn(By, Ax));
+  if (U == 0.0f || V == 0.0f || W == 0.0f) {
+    U = __double2float_rn(__dsub_rn(__dmul_rn((double)Cx, (double)By), __dmul_rn((double)Cy, (double)Bx)));
+    V = __double2float_rn(__dsub_rn(__dmul_rn((double)Ax, (double)Cy), __dmul_rn((double)Ay, (double)Cx)));
+    W = __double2float_rn(__dsub_rn(__dmul_rn((double)Bx, (double)Ay), __dmul_rn((double)By, (double)Ax)));
+  }
+  if ((U < 0.0f || V < 0.0f || W < 0.0f) && (U > 0.0f || V > 0.0f || W > 0.0f)) return false;
+  const float det = __fadd_rn(__fadd_rn(U, V), W);
+  if (det == 0.0f) return false;
+  const float Az = shear_dot(Ax0, Ay0, Az0, s.cz);
+  const float Bz = shear_dot(Bx0, By0, Bz0, s.cz);
+  const float Cz = shear_dot(Cx0, Cy0, Cz0, s.cz);
+  const float T = __fmaf_rn(W, Cz, __fmaf_rn(V, Bz, __fmul_rn(U, Az)));
+  const float rcp = __fdiv_rn(1.0f, det);
+  const float tt = __fmul_rn(T, rcp);
+  if (!(tt > tmin)) return false;
+  if (!(tt < tlim || (allow_equal && tt == tlim))) return false;
+  t = tt;
+  bu = __fmul_rn(V, rcp);
+  bv = __fmul_rn(W, rcp);
+  return true;
+}
+
+// ---- traversal -------------------------------------------------------------------
+FR_D uint32_t sign_extend_s8x4(uint32_t x)
+{
+  uint32_t r;
+  asm("prmt.b32 %0, %1, 0x0, 0x0000BA98;" : "=r"(r) : "r"(x));
+  return r;
+}
+FR_D float byte_f(uint32_t w, int j) { return (float)((w >> (8 * j)) & 0xffu); }
+
+// Short stack kept in shared memory (one column per thread, 8-byte entries, so a
+// warp's accesses are conflict free); deep paths overflow to thread-local memory.
+constexpr int kSmemStack = 12;
+constexpr int kLocalStack = 36;
+
+struct TravStack {
+  uint2* smem;  // &smem_stack[0][thread]
+  int stride;   // threads per block
+  uint2 local[kLocalStack];
+  int sp;
+  FR_D void push(const uint2& e)
+  {
+    if (sp < kSmemStack)
+      smem[sp * stride] = e;
+    else
+      local[sp - kSmemStack] = e;
+    sp++;
+  }
+  FR_D uint2 pop()
+  {
+    sp--;
+    return sp < kSmemStack ? smem[sp * stride] : local[sp - kSmemStack];
+  }
+};
+
+struct TraceCounters {
+  uint32_t nodes, tris;
+};
+
+// Alpha-test hook: returns true if the candidate hit is accepted.  Opaque scenes
+// compile this away.
+struct NoAnyHit {
+  FR_D bool operator()(uint32_t, float, float) const { return true; }
+};
+
+// Closest hit (ANY = false) or first accepted hit (ANY = true).
+// Tie rule on exactly equal t: lower global face index wins (as in the oracle).
+template <bool ANY, bool COUNT, typename AnyHit>
+FR_D HitRecord traverse(const BvhView& bvh, const float3& o, const float3& d, float tmin, float tmax,
+                        TravStack& st, const AnyHit& anyhit, TraceCounters* cnt)
+{
+  HitRecord best;
+  best.t = tmax;
+  best.u = best.v = 0.0f;
+  best.face = kNoHit;
+
+  const RayShear sh = make_shear(d);
+  // box tests are conservative: guard against 0 * inf and widen by a few ulps
+  const float tiny = 1e-30f;
+  const float3 ds = f3(fabsf(d.x) > tiny ? d.x : copysignf(tiny, d.x),
+                       fabsf(d.y) > tiny ? d.y : copysignf(tiny, d.y),
+                       fabsf(d.z) > tiny ? d.z : copysignf(tiny, d.z));
+  const float3 idir = f3(1.0f / ds.x, 1.0f / ds.y, 1.0f / ds.z);
+  const uint32_t octinv = (d.x >= 0.0f ? 1u : 0u) | (d.y >= 0.0f ? 2u : 0u) | (d.z >= 0.0f ? 4u : 0u);
+  const uint32_t octinv4 = octinv * 0x01010101u;
+  constexpr float kFar = 1.0000005f, kNear = 0.9999995f;
+
+  st.sp = 0;
+  uint2 ngroup = make_uint2(0u, 0x80000000u);
+  uint2 tgroup = make_uint2(0u, 0u);
+
+  for (;;) {
+    if (ngroup.y > 0x00ffffffu) {
+      const uint32_t hits_imask = ngroup.y;
+      const uint32_t bit = 31u - __clz(hits_imask);
+      ngroup.y &= ~(1u << bit);
+      if (ngroup.y > 0x00ffffffu) st.push(ngroup);
+      const uint32_t slot = (bit ^ octinv) & 7u;
+      const uint32_t rel = __popc(hits_imask & ~(0xffffffffu << slot));
+      const float4* np = bvh.nodes + 5ull * (ngroup.x + rel);
+      const float4 n0 = __ldg(np + 0), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3),
+                   n4 = __ldg(np + 4);
+      if (COUNT) cnt->nodes++;
+      const uint32_t ew = __float_as_uint(n0.w);
+      const float sx = __uint_as_float((ew & 0xffu) << 23);
+      const float sy = __uint_as_float(((ew >> 8) & 0xffu) << 23);
+      const float sz = __uint_as_float(((ew >> 16) & 0xffu) << 23);
+      const float ax = sx * idir.x, ay = sy * idir.y, az = sz * idir.z;
+      const float bx = (n0.x - o.x) * idir.x, by = (n0.y - o.y) * idir.y, bz = (n0.z - o.z) * idir.z;
+      uint32_t hitmask = 0;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const uint32_t meta4 = __float_as_uint(half == 0 ? n1.z : n1.w);
+        const uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
+        const uint32_t inner_mask4 = sign_extend_s8x4(is_inner4 << 3);
+        const uint32_t bit_index4 = (meta4 ^ (octinv4 & inner_mask4)) & 0x1f1f1f1fu;
+        const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
+        const uint32_t qlox = __float_as_uint(half == 0 ? n2.x : n2.y);
+        const uint32_t qloy = __float_as_uint(half == 0 ? n2.z : n2.w);
+        const uint32_t qloz = __float_as_uint(half == 0 ? n3.x : n3.y);
+        const uint32_t qhix = __float_as_uint(half == 0 ? n3.z : n3.w);
+        const uint32_t qhiy = __float_as_uint(half == 0 ? n4.x : n4.y);
+        const uint32_t qhiz = __float_as_uint(half == 0 ? n4.z : n4.w);
+        const uint32_t nx = d.x < 0.0f ? qhix : qlox, fx = d.x < 0.0f ? qlox : qhix;
+        const uint32_t ny = d.y < 0.0f ? qhiy : qloy, fy = d.y < 0.0f ? qloy : qhiy;
+        const uint32_t nz = d.z < 0.0f ? qhiz : qloz, fz = d.z < 0.0f ? qloz : qhiz;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float t0x = fmaf(byte_f(nx, j), ax, bx), t1x = fmaf(byte_f(fx, j), ax, bx);
+          const float t0y = fmaf(byte_f(ny, j), ay, by), t1y = fmaf(byte_f(fy, j), ay, by);
+          const float t0z = fmaf(byte_f(nz, j), az, bz), t1z = fmaf(byte_f(fz, j), az, bz);
+          const float cnear = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, tmin)) * kNear;
+          const float cfar = fminf(fminf(t1x, t1y), fminf(t1z, best.t)) * kFar;
+          if (cnear <= cfar) {
+            const uint32_t cb = (child_bits4 >> (8 * j)) & 0xffu;
+            const uint32_t bi = (bit_index4 >> (8 * j)) & 0xffu;
+            hitmask |= cb << bi;
+          }
+        }
+      }
+      ngroup.x = __float_as_uint(n1.x);
+      ngroup.y = (hitmask & 0xff000000u) | (ew >> 24);
+      tgroup.x = __float_as_uint(n1.y);
+      tgroup.y = hitmask & 0x00ffffffu;
+    } else {
+      tgroup = ngroup;
+      ngroup = make_uint2(0u, 0u);
+    }
+
+    while (tgroup.y != 0u) {
+      const uint32_t bit = __ffs(tgroup.y) - 1u;
+      tgroup.y &= tgroup.y - 1u;
+      const float4* tp = bvh.tris + 3ull * (tgroup.x + bit);
+      const float4 v0 = __ldg(tp + 0), v1 = __ldg(tp + 1), v2 = __ldg(tp + 2);
+      if (COUNT) cnt->tris++;
+      float t, u, v;
+      if (!watertight_hit(sh, o, v0, v1, v2, tmin, best.t, best.face != kNoHit, t, u, v)) continue;
+      const uint32_t face = __float_as_uint(v0.w);
+      if (t == best.t && best.face != kNoHit && face > best.face) continue;
+      if ((__float_as_uint(v1.w) & 1u) && !anyhit(face, u, v)) continue;
+      best.t = t;
+      best.u = u;
+      best.v = v;
+      best.face = face;
+      if (ANY) return best;
+    }
+
+    if (ngroup.y <= 0x00ffffffu) {
+      if (st.sp == 0) break;
+      ngroup = st.pop();
+    }
+  }
+  return best;
+}
+
+}  // namespace frd

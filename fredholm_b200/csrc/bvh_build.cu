@@ -1,0 +1,477 @@
+// GPU BVH construction: world-space flattening -> 63-bit Morton codes -> radix
+// sort -> Karras (2012) binary radix tree -> bottom-up box fit -> greedy collapse
+// to an 8-wide tree -> CWBVH quantisation (Ylitie et al. 2017).
+//
+// Stands in for the reference's optixAccelBuild calls (per-submesh GAS + one IAS,
+// renderer.h:434-552).  Like the reference on set_time (renderer.h:614-619) the
+// tree is rebuilt, not refitted, when transforms change -- a full build of 1 M
+// triangles is a few milliseconds on a B200.
+#include <cub/device/device_radix_sort.cuh>
+
+#include "bvh_build.h"
+
+namespace frd
+{
+namespace
+{
+
+constexpr int kLeafMax = 3;  // triangles per leaf slot (unary count fits 3 bits)
+
+// ---- stage 1: world-space triangles + scene bounds --------------------------------
+__device__ __forceinline__ float xf_row(const float4& r, const float3& p)
+{
+  // same rounding sequence as the oracle's transform_position (no fused ops)
+  return __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r.x, p.x), __fmul_rn(r.y, p.y)), __fmul_rn(r.z, p.z)),
+                   __fmul_rn(r.w, 1.0f));
+}
+
+__device__ __forceinline__ void atomic_min_f(float* addr, float v)
+{
+  // valid for any sign: compare as ordered ints
+  if (v >= 0.0f)
+    atomicMin(reinterpret_cast<int*>(addr), __float_as_int(v));
+  else
+    atomicMax(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
+__device__ __forceinline__ void atomic_max_f(float* addr, float v)
+{
+  if (v >= 0.0f)
+    atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+  else
+    atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
+
+__global__ void k_world_tris(const float3* __restrict__ vertices, const uint3* __restrict__ indices,
+                             const uint32_t* __restrict__ face_submesh,
+                             const uint32_t* __restrict__ face_flags,
+                             const fredholm::Matrix3x4* __restrict__ o2w, uint32_t n,
+                             float4* __restrict__ wtri, float* __restrict__ bounds6)
+{
+  const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+  float lo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, hi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+  if (f < n) {
+    const uint3 idx = indices[f];
+    const fredholm::Matrix3x4 m = o2w[face_submesh[f]];
+    const uint32_t vid[3] = {idx.x, idx.y, idx.z};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const float3 p = vertices[vid[k]];
+      const float x = xf_row(m.m[0], p), y = xf_row(m.m[1], p), z = xf_row(m.m[2], p);
+      const float w = k == 0 ? __uint_as_float(f) : (k == 1 ? __uint_as_float(face_flags ? face_flags[f] : 0u) : 0.0f);
+      wtri[3ull * f + k] = make_float4(x, y, z, w);
+      lo[0] = fminf(lo[0], x);
+      lo[1] = fminf(lo[1], y);
+      lo[2] = fminf(lo[2], z);
+      hi[0] = fmaxf(hi[0], x);
+      hi[1] = fmaxf(hi[1], y);
+      hi[2] = fmaxf(hi[2], z);
+    }
+  }
+  // warp reduce, one atomic set per warp
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], off));
+      hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], off));
+    }
+  }
+  if ((threadIdx.x & 31) == 0 && lo[0] <= hi[0]) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      atomic_min_f(bounds6 + a, lo[a]);
+      atomic_max_f(bounds6 + 3 + a, hi[a]);
+    }
+  }
+}
+
+// ---- stage 2: Morton codes ------------------------------------------------------------
+__device__ __forceinline__ uint64_t spread21(uint64_t x)
+{
+  x &= 0x1fffffull;
+  x = (x | x << 32) & 0x1f00000000ffffull;
+  x = (x | x << 16) & 0x1f0000ff0000ffull;
+  x = (x | x << 8) & 0x100f00f00f00f00full;
+  x = (x | x << 4) & 0x10c30c30c30c30c3ull;
+  x = (x | x << 2) & 0x1249249249249249ull;
+  return x;
+}
+
+__global__ void k_morton(const float4* __restrict__ wtri, const float* __restrict__ bounds6, uint32_t n,
+                         uint64_t* __restrict__ keys, uint32_t* __restrict__ vals)
+{
+  const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= n) return;
+  const float4 a = wtri[3ull * f], b = wtri[3ull * f + 1], c = wtri[3ull * f + 2];
+  const float cx = 0.5f * (fminf(fminf(a.x, b.x), c.x) + fmaxf(fmaxf(a.x, b.x), c.x));
+  const float cy = 0.5f * (fminf(fminf(a.y, b.y), c.y) + fmaxf(fmaxf(a.y, b.y), c.y));
+  const float cz = 0.5f * (fminf(fminf(a.z, b.z), c.z) + fmaxf(fmaxf(a.z, b.z), c.z));
+  const float ex = fmaxf(bounds6[3] - bounds6[0], 1e-30f);
+  const float ey = fmaxf(bounds6[4] - bounds6[1], 1e-30f);
+  const float ez = fmaxf(bounds6[5] - bounds6[2], 1e-30f);
+  // one grid step for all axes keeps cells cubic (better trees for flat scenes)
+  const float e = fmaxf(ex, fmaxf(ey, ez));
+  const float s = 2097151.0f / e;
+  const uint64_t qx = (uint64_t)fminf(fmaxf((cx - bounds6[0]) * s, 0.0f), 2097151.0f);
+  const uint64_t qy = (uint64_t)fminf(fmaxf((cy - bounds6[1]) * s, 0.0f), 2097151.0f);
+  const uint64_t qz = (uint64_t)fminf(fmaxf((cz - bounds6[2]) * s, 0.0f), 2097151.0f);
+  keys[f] = spread21(qx) | (spread21(qy) << 1) | (spread21(qz) << 2);
+  vals[f] = f;
+}
+
+// ---- stage 3: Karras binary radix tree -------------------------------------------------
+// node ids: internal i -> i (0..n-2), leaf j -> (n-1)+j
+struct Lbvh {
+  uint2* child;        // [n-1] left/right node ids
+  uint32_t* parent;    // [2n-1]
+  uint2* range;        // [n-1] first,last sorted leaf covered
+  float4* lo;          // [2n-1]
+  float4* hi;          // [2n-1]
+  uint32_t* visit;     // [n-1]
+};
+
+__device__ __forceinline__ int delta(const uint64_t* keys, int n, int i, int j)
+{
+  if (j < 0 || j >= n) return -1;
+  const uint64_t a = keys[i], b = keys[j];
+  if (a == b) return 64 + __clz(i ^ j);
+  return __clzll(a ^ b);
+}
+
+__global__ void k_karras(const uint64_t* __restrict__ keys, int n, Lbvh t)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n - 1) return;
+  const int d = (delta(keys, n, i, i + 1) - delta(keys, n, i, i - 1)) >= 0 ? 1 : -1;
+  const int dmin = delta(keys, n, i, i - d);
+  int lmax = 2;
+  while (delta(keys, n, i, i + lmax * d) > dmin) lmax *= 2;
+  int l = 0;
+  for (int s = lmax / 2; s >= 1; s /= 2)
+    if (delta(keys, n, i, i + (l + s) * d) > dmin) l += s;
+  const int j = i + l * d;
+  const int dnode = delta(keys, n, i, j);
+  int s = 0;
+  int tt = l;
+  do {
+    tt = (tt + 1) / 2;
+    if (delta(keys, n, i, i + (s + tt) * d) > dnode) s += tt;
+  } while (tt > 1);
+  const int gamma = i + s * d + min(d, 0);
+  const int first = min(i, j), last = max(i, j);
+  const uint32_t left = (first == gamma) ? (uint32_t)(n - 1 + gamma) : (uint32_t)gamma;
+  const uint32_t right = (last == gamma + 1) ? (uint32_t)(n - 1 + gamma + 1) : (uint32_t)(gamma + 1);
+  t.child[i] = make_uint2(left, right);
+  t.range[i] = make_uint2((uint32_t)first, (uint32_t)last);
+  t.parent[left] = i;
+  t.parent[right] = i;
+  if (i == 0) t.parent[0] = 0xffffffffu;
+}
+
+// ---- stage 4: bottom-up fit ----------------------------------------------------------------
+__global__ void k_fit(const float4* __restrict__ wtri, const uint32_t* __restrict__ sorted, int n, Lbvh t)
+{
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const uint32_t f = sorted[j];
+  const float4 a = wtri[3ull * f], b = wtri[3ull * f + 1], c = wtri[3ull * f + 2];
+  float4 lo = make_float4(fminf(fminf(a.x, b.x), c.x), fminf(fminf(a.y, b.y), c.y), fminf(fminf(a.z, b.z), c.z), 0.0f);
+  float4 hi = make_float4(fmaxf(fmaxf(a.x, b.x), c.x), fmaxf(fmaxf(a.y, b.y), c.y), fmaxf(fmaxf(a.z, b.z), c.z), 0.0f);
+  const uint32_t leaf = n - 1 + j;
+  t.lo[leaf] = lo;
+  t.hi[leaf] = hi;
+  if (n == 1) return;
+  uint32_t cur = t.parent[leaf];
+  for (;;) {
+    __threadfence();
+    if (atomicAdd(&t.visit[cur], 1u) == 0u) return;  // sibling not done yet
+    const uint2 ch = t.child[cur];
+    const volatile float4* vlo = t.lo;
+    const volatile float4* vhi = t.hi;
+    const float4 l0 = make_float4(vlo[ch.x].x, vlo[ch.x].y, vlo[ch.x].z, 0.f);
+    const float4 l1 = make_float4(vlo[ch.y].x, vlo[ch.y].y, vlo[ch.y].z, 0.f);
+    const float4 h0 = make_float4(vhi[ch.x].x, vhi[ch.x].y, vhi[ch.x].z, 0.f);
+    const float4 h1 = make_float4(vhi[ch.y].x, vhi[ch.y].y, vhi[ch.y].z, 0.f);
+    lo = make_float4(fminf(l0.x, l1.x), fminf(l0.y, l1.y), fminf(l0.z, l1.z), 0.0f);
+    hi = make_float4(fmaxf(h0.x, h1.x), fmaxf(h0.y, h1.y), fmaxf(h0.z, h1.z), 0.0f);
+    t.lo[cur] = lo;
+    t.hi[cur] = hi;
+    if (cur == 0) return;
+    cur = t.parent[cur];
+  }
+}
+
+// ---- stage 5: collapse to 8-wide + quantise --------------------------------------------------
+__device__ __forceinline__ uint32_t tri_count(const Lbvh& t, int n, uint32_t id)
+{
+  if (id >= (uint32_t)(n - 1)) return 1u;
+  const uint2 r = t.range[id];
+  return r.y - r.x + 1u;
+}
+__device__ __forceinline__ uint32_t first_leaf(const Lbvh& t, int n, uint32_t id)
+{
+  return id >= (uint32_t)(n - 1) ? id - (uint32_t)(n - 1) : t.range[id].x;
+}
+__device__ __forceinline__ float half_area(const float4& lo, const float4& hi)
+{
+  const float ex = hi.x - lo.x, ey = hi.y - lo.y, ez = hi.z - lo.z;
+  return ex * ey + ey * ez + ez * ex;
+}
+
+// biased exponent e such that extent <= 255 * 2^(e-127)
+__device__ __forceinline__ uint32_t grid_exponent(float extent)
+{
+  const float step = __fdiv_ru(extent, 255.0f);
+  uint32_t e = (__float_as_uint(step) + 0x007fffffu) >> 23;
+  return min(max(e, 1u), 254u);
+}
+
+struct CollapseCounters {
+  uint32_t n_nodes;
+  uint32_t n_tris;
+};
+
+__global__ void k_collapse(uint32_t level_begin, uint32_t level_end, uint32_t* __restrict__ work, int n,
+                           Lbvh t, const float4* __restrict__ wtri, const uint32_t* __restrict__ sorted,
+                           CollapseCounters* __restrict__ counters, Node8* __restrict__ nodes,
+                           float4* __restrict__ tris)
+{
+  const uint32_t n8 = level_begin + blockIdx.x * blockDim.x + threadIdx.x;
+  if (n8 >= level_end) return;
+  const uint32_t b2 = work[n8];
+
+  uint32_t c[8];
+  int nc;
+  const bool root_is_cluster = tri_count(t, n, b2) <= (uint32_t)kLeafMax;  // only for tiny scenes
+  if (root_is_cluster) {
+    c[0] = b2;
+    nc = 1;
+  } else {
+    const uint2 ch = t.child[b2];
+    c[0] = ch.x;
+    c[1] = ch.y;
+    nc = 2;
+    while (nc < 8) {
+      int best = -1;
+      float best_area = -1.0f;
+      for (int k = 0; k < nc; ++k) {
+        if (tri_count(t, n, c[k]) > (uint32_t)kLeafMax) {
+          const float a = half_area(t.lo[c[k]], t.hi[c[k]]);
+          if (a > best_area) {
+            best_area = a;
+            best = k;
+          }
+        }
+      }
+      if (best < 0) break;
+      const uint2 ch2 = t.child[c[best]];
+      c[best] = ch2.x;
+      c[nc++] = ch2.y;
+    }
+  }
+
+  const float4 nlo = t.lo[b2], nhi = t.hi[b2];
+  const float3 ncen = f3(0.5f * (nlo.x + nhi.x), 0.5f * (nlo.y + nhi.y), 0.5f * (nlo.z + nhi.z));
+
+  // greedy octant-order slot assignment (Ylitie et al. sec. 4.2)
+  float cost[8][8];
+  for (int k = 0; k < nc; ++k) {
+    const float4 l = t.lo[c[k]], h = t.hi[c[k]];
+    const float3 dc = f3(0.5f * (l.x + h.x) - ncen.x, 0.5f * (l.y + h.y) - ncen.y, 0.5f * (l.z + h.z) - ncen.z);
+    for (int s = 0; s < 8; ++s) {
+      cost[k][s] = ((s & 1) ? dc.x : -dc.x) + ((s & 2) ? dc.y : -dc.y) + ((s & 4) ? dc.z : -dc.z);
+    }
+  }
+  int slot_of[8];
+  int child_at[8];
+  for (int s = 0; s < 8; ++s) child_at[s] = -1;
+  for (int k = 0; k < 8; ++k) slot_of[k] = -1;
+  for (int it = 0; it < nc; ++it) {
+    int bk = -1, bs = -1;
+    float bc = -3.0e38f;
+    for (int k = 0; k < nc; ++k) {
+      if (slot_of[k] >= 0) continue;
+      for (int s = 0; s < 8; ++s) {
+        if (child_at[s] >= 0) continue;
+        if (cost[k][s] > bc) {
+          bc = cost[k][s];
+          bk = k;
+          bs = s;
+        }
+      }
+    }
+    slot_of[bk] = bs;
+    child_at[bs] = bk;
+  }
+
+  uint32_t n_inner = 0, n_leaf_tris = 0;
+  for (int k = 0; k < nc; ++k) {
+    const uint32_t cnt = tri_count(t, n, c[k]);
+    if (cnt > (uint32_t)kLeafMax)
+      n_inner++;
+    else
+      n_leaf_tris += cnt;
+  }
+  const uint32_t cbase = n_inner ? atomicAdd(&counters->n_nodes, n_inner) : 0u;
+  const uint32_t tbase = n_leaf_tris ? atomicAdd(&counters->n_tris, n_leaf_tris) : 0u;
+
+  Node8 out;
+  out.px = nlo.x;
+  out.py = nlo.y;
+  out.pz = nlo.z;
+  const uint32_t ex = grid_exponent(__fsub_ru(nhi.x, nlo.x)), ey = grid_exponent(__fsub_ru(nhi.y, nlo.y)),
+                 ez = grid_exponent(__fsub_ru(nhi.z, nlo.z));
+  out.ex = (uint8_t)ex;
+  out.ey = (uint8_t)ey;
+  out.ez = (uint8_t)ez;
+  out.imask = 0;
+  out.child_base = cbase;
+  out.tri_base = tbase;
+  // 1 / 2^(e-127) = 2^(127-e) -> biased exponent 254 - e
+  const float isx = __uint_as_float((254u - ex) << 23), isy = __uint_as_float((254u - ey) << 23),
+              isz = __uint_as_float((254u - ez) << 23);
+  uint32_t rank = 0, toff = 0;
+  for (int s = 0; s < 8; ++s) {
+    const int k = child_at[s];
+    if (k < 0) {
+      out.meta[s] = 0;
+      out.qlox[s] = out.qloy[s] = out.qloz[s] = 255;
+      out.qhix[s] = out.qhiy[s] = out.qhiz[s] = 0;
+      continue;
+    }
+    const uint32_t id = c[k];
+    const uint32_t cnt = tri_count(t, n, id);
+    const float4 l = t.lo[id], h = t.hi[id];
+    // conservative: lower bounds round down, upper bounds round up
+    out.qlox[s] = (uint8_t)fminf(fmaxf(floorf(__fmul_rd(__fsub_rd(l.x, nlo.x), isx)), 0.0f), 255.0f);
+    out.qloy[s] = (uint8_t)fminf(fmaxf(floorf(__fmul_rd(__fsub_rd(l.y, nlo.y), isy)), 0.0f), 255.0f);
+    out.qloz[s] = (uint8_t)fminf(fmaxf(floorf(__fmul_rd(__fsub_rd(l.z, nlo.z), isz)), 0.0f), 255.0f);
+    out.qhix[s] = (uint8_t)fminf(fmaxf(ceilf(__fmul_ru(__fsub_ru(h.x, nlo.x), isx)), 0.0f), 255.0f);
+    out.qhiy[s] = (uint8_t)fminf(fmaxf(ceilf(__fmul_ru(__fsub_ru(h.y, nlo.y), isy)), 0.0f), 255.0f);
+    out.qhiz[s] = (uint8_t)fminf(fmaxf(ceilf(__fmul_ru(__fsub_ru(h.z, nlo.z), isz)), 0.0f), 255.0f);
+    if (cnt > (uint32_t)kLeafMax) {
+      out.imask |= (uint8_t)(1u << s);
+      out.meta[s] = (uint8_t)(0x20u | (24u + s));
+      work[cbase + rank] = id;
+      rank++;
+    } else {
+      const uint32_t unary = cnt == 1 ? 1u : (cnt == 2 ? 3u : 7u);
+      out.meta[s] = (uint8_t)((unary << 5) | toff);
+      const uint32_t first = first_leaf(t, n, id);
+      for (uint32_t q = 0; q < cnt; ++q) {
+        const uint32_t f = sorted[first + q];
+        float4* dst = tris + 3ull * (tbase + toff + q);
+        dst[0] = wtri[3ull * f];
+        dst[1] = wtri[3ull * f + 1];
+        dst[2] = wtri[3ull * f + 2];
+      }
+      toff += cnt;
+    }
+  }
+  nodes[n8] = out;
+}
+
+__global__ void k_empty_root(Node8* nodes)
+{
+  Node8 out = {};
+  out.ex = out.ey = out.ez = 127;
+  for (int s = 0; s < 8; ++s) {
+    out.qlox[s] = out.qloy[s] = out.qloz[s] = 255;
+  }
+  nodes[0] = out;
+}
+
+}  // namespace
+
+void build_bvh(cudaStream_t stream, const float3* d_vertices, const uint3* d_indices,
+               const uint32_t* d_face_submesh, const uint32_t* d_face_flags,
+               const fredholm::Matrix3x4* d_o2w, uint32_t n_faces, DeviceBvh& out)
+{
+  out.n_faces = n_faces;
+  out.depth = 1;
+  if (n_faces == 0) {
+    out.nodes.alloc(1);
+    out.tris.alloc(3);
+    out.n_nodes = 1;
+    k_empty_root<<<1, 1, 0, stream>>>(out.nodes.get());
+    FR_CUDA_LAUNCH_CHECK();
+    FR_CUDA_CHECK(cudaStreamSynchronize(stream));
+    return;
+  }
+  const int n = (int)n_faces;
+  const int B = 256;
+  const int G = (n + B - 1) / B;
+
+  DevBuf<float4> wtri(3ull * n);
+  DevBuf<float> bounds(6);
+  const float init_b[6] = {3.0e38f, 3.0e38f, 3.0e38f, -3.0e38f, -3.0e38f, -3.0e38f};
+  FR_CUDA_CHECK(cudaMemcpyAsync(bounds.get(), init_b, sizeof(init_b), cudaMemcpyHostToDevice, stream));
+  k_world_tris<<<G, B, 0, stream>>>(d_vertices, d_indices, d_face_submesh, d_face_flags, d_o2w, n_faces,
+                                    wtri.get(), bounds.get());
+  FR_CUDA_LAUNCH_CHECK();
+
+  DevBuf<uint64_t> keys(n), keys_sorted(n);
+  DevBuf<uint32_t> vals(n), sorted(n);
+  k_morton<<<G, B, 0, stream>>>(wtri.get(), bounds.get(), n_faces, keys.get(), vals.get());
+  FR_CUDA_LAUNCH_CHECK();
+  size_t tmp_bytes = 0;
+  FR_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys.get(), keys_sorted.get(), vals.get(),
+                                                sorted.get(), n, 0, 63, stream));
+  DevBuf<unsigned char> tmp(tmp_bytes);
+  FR_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(tmp.get(), tmp_bytes, keys.get(), keys_sorted.get(), vals.get(),
+                                                sorted.get(), n, 0, 63, stream));
+
+  const int n_int = n > 1 ? n - 1 : 1;
+  DevBuf<uint2> child(n_int), range(n_int);
+  DevBuf<uint32_t> parent(2ull * n), visit(n_int);
+  DevBuf<float4> lo(2ull * n), hi(2ull * n);
+  visit.zero(stream);
+  Lbvh t{child.get(), parent.get(), range.get(), lo.get(), hi.get(), visit.get()};
+  if (n > 1) {
+    k_karras<<<(n - 1 + B - 1) / B, B, 0, stream>>>(keys_sorted.get(), n, t);
+    FR_CUDA_LAUNCH_CHECK();
+  }
+  k_fit<<<G, B, 0, stream>>>(wtri.get(), sorted.get(), n, t);
+  FR_CUDA_LAUNCH_CHECK();
+
+  // collapse, level by level; node n8 is built from binary node work[n8]
+  const size_t max_nodes = (size_t)n / 2 + 2;
+  DevBuf<Node8> nodes(max_nodes);
+  DevBuf<uint32_t> work(max_nodes);
+  out.tris.alloc(3ull * n);
+  DevBuf<CollapseCounters> counters(1);
+  const CollapseCounters init_c{1u, 0u};
+  const uint32_t root_id = n > 1 ? 0u : 0u;  // n == 1: leaf 0 has node id (n-1)+0 = 0
+  FR_CUDA_CHECK(cudaMemcpyAsync(counters.get(), &init_c, sizeof(init_c), cudaMemcpyHostToDevice, stream));
+  FR_CUDA_CHECK(cudaMemcpyAsync(work.get(), &root_id, sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+  uint32_t begin = 0, end = 1, depth = 0;
+  while (begin < end) {
+    const uint32_t cnt = end - begin;
+    k_collapse<<<(cnt + 63) / 64, 64, 0, stream>>>(begin, end, work.get(), n, t, wtri.get(), sorted.get(),
+                                                    counters.get(), nodes.get(), out.tris.get());
+    FR_CUDA_LAUNCH_CHECK();
+    CollapseCounters h;
+    FR_CUDA_CHECK(cudaMemcpyAsync(&h, counters.get(), sizeof(h), cudaMemcpyDeviceToHost, stream));
+    FR_CUDA_CHECK(cudaStreamSynchronize(stream));
+    if (h.n_nodes > max_nodes) throw std::runtime_error("bvh collapse: node pool overflow");
+    begin = end;
+    end = h.n_nodes;
+    depth++;
+  }
+  out.depth = depth;
+  out.n_nodes = end;
+  // shrink the node pool to its final size
+  out.nodes.alloc(end);
+  FR_CUDA_CHECK(cudaMemcpyAsync(out.nodes.get(), nodes.get(), sizeof(Node8) * end, cudaMemcpyDeviceToDevice, stream));
+  float hb[6];
+  FR_CUDA_CHECK(cudaMemcpyAsync(hb, bounds.get(), sizeof(hb), cudaMemcpyDeviceToHost, stream));
+  FR_CUDA_CHECK(cudaStreamSynchronize(stream));
+  for (int a = 0; a < 3; ++a) {
+    out.bounds_lo[a] = hb[a];
+    out.bounds_hi[a] = hb[3 + a];
+  }
+  if (depth + 2 > (uint32_t)(kSmemStack + kLocalStack))
+    throw std::runtime_error("bvh: tree too deep for the traversal stack");
+}
+
+}  // namespace frd

@@ -1,0 +1,555 @@
+// extern "C" facade over fredholm::Renderer (see include/fredholm_b200.h).
+#include "fredholm_b200.h"
+
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "kernels/post-process.h"
+#include "renderer_impl.h"
+
+using namespace fredholm;
+
+struct fr_renderer {
+  Renderer renderer;
+  std::vector<Texture> staged_textures;
+  // device layers owned by fr_render_frame_host
+  frd::DevBuf<float4> h_beauty, h_position, h_normal, h_texcoord, h_albedo;
+  frd::DevBuf<float> h_depth;
+  explicit fr_renderer(int dev) : renderer(dev) {}
+};
+
+struct fr_scene {
+  Scene scene;
+};
+
+namespace
+{
+thread_local std::string g_error;
+
+template <typename F>
+int guarded(F&& f)
+{
+  try {
+    f();
+    return 0;
+  } catch (const std::exception& e) {
+    g_error = e.what();
+  } catch (...) {
+    g_error = "unknown error";
+  }
+  return -1;
+}
+
+CameraParams make_camera(const float* t12, float fov, float F, float focus)
+{
+  CameraParams c;
+  std::memcpy(&c.transform, t12, sizeof(float) * 12);
+  c.fov = fov;
+  c.F = F;
+  c.focus = focus;
+  return c;
+}
+
+RenderLayer make_layers(const fr_layers* l)
+{
+  RenderLayer r;
+  r.beauty = static_cast<float4*>(l->beauty);
+  r.position = static_cast<float4*>(l->position);
+  r.depth = static_cast<float*>(l->depth);
+  r.normal = static_cast<float4*>(l->normal);
+  r.texcoord = static_cast<float4*>(l->texcoord);
+  r.albedo = static_cast<float4*>(l->albedo);
+  return r;
+}
+
+void camera_rows(const Camera& cam, float* out12) { cam.to_rows(out12); }
+
+void scene_sizes(const Scene& s, uint32_t* out6)
+{
+  out6[0] = (uint32_t)s.m_vertices.size();
+  out6[1] = (uint32_t)s.m_indices.size();
+  out6[2] = (uint32_t)s.m_materials.size();
+  out6[3] = (uint32_t)s.m_textures.size();
+  out6[4] = (uint32_t)s.m_submesh_offsets.size();
+  out6[5] = s.m_has_camera_transform ? 1u : 0u;
+}
+
+void scene_arrays(const Scene& s, float* vertices, float* normals, float* texcoords, uint32_t* indices,
+                  uint32_t* material_ids, uint32_t* instance_ids, void* materials, uint32_t* submesh_offsets,
+                  uint32_t* submesh_n_faces, float* transforms, float* camera_transform16)
+{
+  std::memcpy(vertices, s.m_vertices.data(), sizeof(float3) * s.m_vertices.size());
+  std::memcpy(normals, s.m_normals.data(), sizeof(float3) * s.m_normals.size());
+  std::memcpy(texcoords, s.m_texcoords.data(), sizeof(float2) * s.m_texcoords.size());
+  std::memcpy(indices, s.m_indices.data(), sizeof(uint3) * s.m_indices.size());
+  std::memcpy(material_ids, s.m_material_ids.data(), 4 * s.m_material_ids.size());
+  std::memcpy(instance_ids, s.m_instance_ids.data(), 4 * s.m_instance_ids.size());
+  std::memcpy(materials, s.m_materials.data(), sizeof(Material) * s.m_materials.size());
+  std::memcpy(submesh_offsets, s.m_submesh_offsets.data(), 4 * s.m_submesh_offsets.size());
+  std::memcpy(submesh_n_faces, s.m_submesh_n_faces.data(), 4 * s.m_submesh_n_faces.size());
+  std::memcpy(transforms, s.m_transforms.data(), 64 * s.m_transforms.size());
+  std::memcpy(camera_transform16, &s.m_camera_transform, 64);
+}
+
+void texture_info(const Scene& s, uint32_t i, uint32_t* width, uint32_t* height, uint32_t* is_color)
+{
+  const Texture& t = s.m_textures.at(i);
+  *width = t.m_width;
+  *height = t.m_height;
+  *is_color = t.m_texture_type == TextureType::COLOR;
+}
+
+void texture_data(const Scene& s, uint32_t i, uint8_t* rgba8)
+{
+  const Texture& t = s.m_textures.at(i);
+  std::memcpy(rgba8, t.m_data.data(), 4 * (size_t)t.m_width * t.m_height);
+}
+}  // namespace
+
+extern "C" {
+
+const char* fr_last_error(void) { return g_error.c_str(); }
+
+int fr_device_count(void)
+{
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+const char* fr_version(void) { return "fredholm_b200 0.1.0 sm_100a"; }
+
+fr_renderer* fr_renderer_create(int cuda_device)
+{
+  fr_renderer* r = nullptr;
+  if (guarded([&] { r = new fr_renderer(cuda_device); }) != 0) return nullptr;
+  return r;
+}
+
+void fr_renderer_destroy(fr_renderer* r)
+{
+  guarded([&] { delete r; });
+}
+
+int fr_load_scene(fr_renderer* r, const char* path, int clear)
+{
+  return guarded([&] { r->renderer.load_scene(path, clear != 0); });
+}
+
+int fr_stage_texture(fr_renderer* r, const uint8_t* rgba8, uint32_t width, uint32_t height, int is_color)
+{
+  int id = -1;
+  const int rc = guarded([&] {
+    r->staged_textures.emplace_back(width, height, reinterpret_cast<const uchar4*>(rgba8),
+                                    is_color ? TextureType::COLOR : TextureType::NONCOLOR);
+    id = (int)r->staged_textures.size() - 1;
+  });
+  return rc == 0 ? id : -1;
+}
+
+int fr_set_scene_arrays(fr_renderer* r, const float* vertices, const float* normals, const float* texcoords,
+                        uint32_t n_vertices, const uint32_t* indices, const uint32_t* material_ids,
+                        const uint32_t* instance_ids, uint32_t n_faces, const void* materials, uint32_t n_materials,
+                        const uint32_t* submesh_offsets, const uint32_t* submesh_n_faces, const float* transforms,
+                        uint32_t n_submeshes)
+{
+  return guarded([&] {
+    Scene s;
+    s.m_vertices.resize(n_vertices);
+    s.m_normals.resize(n_vertices);
+    s.m_texcoords.resize(n_vertices);
+    std::memcpy(s.m_vertices.data(), vertices, sizeof(float3) * n_vertices);
+    std::memcpy(s.m_normals.data(), normals, sizeof(float3) * n_vertices);
+    std::memcpy(s.m_texcoords.data(), texcoords, sizeof(float2) * n_vertices);
+    s.m_indices.resize(n_faces);
+    std::memcpy(s.m_indices.data(), indices, sizeof(uint3) * n_faces);
+    s.m_material_ids.assign(material_ids, material_ids + n_faces);
+    s.m_instance_ids.assign(instance_ids, instance_ids + n_faces);
+    s.m_materials.resize(n_materials);
+    std::memcpy(s.m_materials.data(), materials, sizeof(Material) * n_materials);
+    s.m_submesh_offsets.assign(submesh_offsets, submesh_offsets + n_submeshes);
+    s.m_submesh_n_faces.assign(submesh_n_faces, submesh_n_faces + n_submeshes);
+    s.m_transforms.resize(n_submeshes);
+    std::memcpy(s.m_transforms.data(), transforms, sizeof(float) * 16 * n_submeshes);
+    s.m_textures = std::move(r->staged_textures);
+    r->staged_textures.clear();
+    r->renderer.set_scene(s);
+  });
+}
+
+int fr_get_scene_sizes(fr_renderer* r, uint32_t* out6)
+{
+  return guarded([&] { scene_sizes(r->renderer.get_scene(), out6); });
+}
+
+int fr_get_scene_arrays(fr_renderer* r, float* vertices, float* normals, float* texcoords, uint32_t* indices,
+                        uint32_t* material_ids, uint32_t* instance_ids, void* materials, uint32_t* submesh_offsets,
+                        uint32_t* submesh_n_faces, float* transforms, float* camera_transform16)
+{
+  return guarded([&] {
+    scene_arrays(r->renderer.get_scene(), vertices, normals, texcoords, indices, material_ids, instance_ids,
+                 materials, submesh_offsets, submesh_n_faces, transforms, camera_transform16);
+  });
+}
+
+int fr_get_texture_info(fr_renderer* r, uint32_t i, uint32_t* width, uint32_t* height, uint32_t* is_color)
+{
+  return guarded([&] { texture_info(r->renderer.get_scene(), i, width, height, is_color); });
+}
+
+int fr_get_texture_data(fr_renderer* r, uint32_t i, uint8_t* rgba8)
+{
+  return guarded([&] { texture_data(r->renderer.get_scene(), i, rgba8); });
+}
+
+fr_scene* fr_scene_create(void)
+{
+  fr_scene* s = nullptr;
+  if (guarded([&] { s = new fr_scene(); }) != 0) return nullptr;
+  return s;
+}
+void fr_scene_destroy(fr_scene* s) { delete s; }
+int fr_scene_load(fr_scene* s, const char* path, int clear)
+{
+  return guarded([&] {
+    s->scene.load_model(path, clear != 0);
+    if (!s->scene.is_valid()) throw std::runtime_error("invalid scene");
+  });
+}
+int fr_scene_get_sizes(fr_scene* s, uint32_t* out6)
+{
+  return guarded([&] { scene_sizes(s->scene, out6); });
+}
+int fr_scene_get_arrays(fr_scene* s, float* vertices, float* normals, float* texcoords, uint32_t* indices,
+                        uint32_t* material_ids, uint32_t* instance_ids, void* materials, uint32_t* submesh_offsets,
+                        uint32_t* submesh_n_faces, float* transforms, float* camera_transform16)
+{
+  return guarded([&] {
+    scene_arrays(s->scene, vertices, normals, texcoords, indices, material_ids, instance_ids, materials,
+                 submesh_offsets, submesh_n_faces, transforms, camera_transform16);
+  });
+}
+int fr_scene_get_texture_info(fr_scene* s, uint32_t i, uint32_t* width, uint32_t* height, uint32_t* is_color)
+{
+  return guarded([&] { texture_info(s->scene, i, width, height, is_color); });
+}
+int fr_scene_get_texture_data(fr_scene* s, uint32_t i, uint8_t* rgba8)
+{
+  return guarded([&] { texture_data(s->scene, i, rgba8); });
+}
+int fr_scene_update_animation(fr_scene* s, float time)
+{
+  return guarded([&] { s->scene.update_animation(time); });
+}
+int fr_set_scene(fr_renderer* r, const fr_scene* s)
+{
+  return guarded([&] { r->renderer.set_scene(s->scene); });
+}
+
+int fr_build_accel(fr_renderer* r)
+{
+  return guarded([&] {
+    r->renderer.build_gas();
+    r->renderer.build_ias();
+  });
+}
+
+int fr_get_accel_info(fr_renderer* r, uint32_t* out3, float* build_ms, uint64_t* bytes)
+{
+  return guarded([&] {
+    const AccelInfo a = r->renderer.get_accel_info();
+    out3[0] = a.n_faces;
+    out3[1] = a.n_nodes;
+    out3[2] = a.depth;
+    if (build_ms) *build_ms = a.build_ms;
+    if (bytes) *bytes = a.bytes;
+  });
+}
+
+int fr_set_time(fr_renderer* r, float time)
+{
+  return guarded([&] { r->renderer.set_time(time); });
+}
+
+int fr_set_transforms(fr_renderer* r, const float* transforms, uint32_t n_submeshes)
+{
+  return guarded([&] {
+    Renderer::Impl* im = r->renderer.impl();
+    if (n_submeshes != im->scene.m_transforms.size()) throw std::runtime_error("transform count mismatch");
+    std::memcpy(im->scene.m_transforms.data(), transforms, sizeof(float) * 16 * n_submeshes);
+    im->upload_transforms();
+    im->build_accel();
+  });
+}
+
+int fr_set_directional_light(fr_renderer* r, const float* le3, const float* dir3, float angle_deg)
+{
+  return guarded([&] {
+    r->renderer.set_directional_light(make_float3(le3[0], le3[1], le3[2]), make_float3(dir3[0], dir3[1], dir3[2]),
+                                      angle_deg);
+  });
+}
+int fr_clear_directional_light(fr_renderer* r)
+{
+  return guarded([&] { r->renderer.clear_directional_light(); });
+}
+int fr_set_sky_intensity(fr_renderer* r, float v)
+{
+  return guarded([&] { r->renderer.set_sky_intensity(v); });
+}
+int fr_load_arhosek_sky(fr_renderer* r, float turbidity, float albedo)
+{
+  return guarded([&] { r->renderer.load_arhosek_sky(turbidity, albedo); });
+}
+int fr_clear_arhosek_sky(fr_renderer* r)
+{
+  return guarded([&] { r->renderer.clear_arhosek_sky(); });
+}
+int fr_set_ibl(fr_renderer* r, const float* rgba32f, uint32_t width, uint32_t height)
+{
+  return guarded([&] { r->renderer.set_ibl(reinterpret_cast<const float4*>(rgba32f), width, height); });
+}
+int fr_load_ibl(fr_renderer* r, const char* path)
+{
+  return guarded([&] { r->renderer.load_ibl(path); });
+}
+int fr_clear_ibl(fr_renderer* r)
+{
+  return guarded([&] { r->renderer.clear_ibl(); });
+}
+
+int fr_set_resolution(fr_renderer* r, uint32_t width, uint32_t height)
+{
+  return guarded([&] { r->renderer.set_resolution(width, height); });
+}
+int fr_init_render_states(fr_renderer* r)
+{
+  return guarded([&] { r->renderer.init_render_states(); });
+}
+int fr_set_sample_offset(fr_renderer* r, uint32_t first_sample)
+{
+  return guarded([&] { r->renderer.set_sample_offset(first_sample); });
+}
+uint32_t fr_get_sample_count(fr_renderer* r) { return r->renderer.get_sample_count(); }
+int fr_set_film_mode(fr_renderer* r, int mode)
+{
+  return guarded([&] { r->renderer.set_film_mode(mode == 0 ? FilmMode::MEAN : FilmMode::SUM); });
+}
+int fr_set_max_wave_paths(fr_renderer* r, uint64_t n_paths)
+{
+  return guarded([&] { r->renderer.set_max_wave_paths((size_t)n_paths); });
+}
+
+int fr_render(fr_renderer* r, const float* camera_transform12, float fov, float F, float focus, const float* bg,
+              const fr_layers* layers_dev, uint32_t n_samples, uint32_t max_depth)
+{
+  return guarded([&] {
+    if (!layers_dev || !layers_dev->beauty) throw std::runtime_error("fr_render: beauty layer is required");
+    r->renderer.render(make_camera(camera_transform12, fov, F, focus), make_float3(bg[0], bg[1], bg[2]),
+                       make_layers(layers_dev), n_samples, max_depth);
+  });
+}
+
+int fr_wait(fr_renderer* r)
+{
+  return guarded([&] { r->renderer.wait_for_completion(); });
+}
+
+int fr_render_frame_host(fr_renderer* r, const float* camera_transform12, float fov, float F, float focus,
+                         const float* bg, const fr_layers* layers_host, uint32_t n_samples, uint32_t max_depth)
+{
+  return guarded([&] {
+    if (!layers_host || !layers_host->beauty) throw std::runtime_error("fr_render_frame_host: beauty is required");
+    Renderer::Impl* im = r->renderer.impl();
+    const size_t n = (size_t)im->width * im->height;
+    cudaStream_t s = im->stream;
+    auto prep4 = [&](frd::DevBuf<float4>& b, bool want) -> float4* {
+      if (!want) return nullptr;
+      b.reserve(n);
+      FR_CUDA_CHECK(cudaMemsetAsync(b.get(), 0, sizeof(float4) * n, s));
+      return b.get();
+    };
+    RenderLayer L;
+    L.beauty = prep4(r->h_beauty, true);
+    L.position = prep4(r->h_position, layers_host->position != nullptr);
+    L.normal = prep4(r->h_normal, layers_host->normal != nullptr);
+    L.texcoord = prep4(r->h_texcoord, layers_host->texcoord != nullptr);
+    L.albedo = prep4(r->h_albedo, layers_host->albedo != nullptr);
+    L.depth = nullptr;
+    if (layers_host->depth) {
+      r->h_depth.reserve(n);
+      FR_CUDA_CHECK(cudaMemsetAsync(r->h_depth.get(), 0, sizeof(float) * n, s));
+      L.depth = r->h_depth.get();
+    }
+    r->renderer.init_render_states();
+    r->renderer.render(make_camera(camera_transform12, fov, F, focus), make_float3(bg[0], bg[1], bg[2]), L, n_samples,
+                       max_depth);
+    auto back = [&](void* dst, const void* src, size_t bytes) {
+      if (dst) FR_CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, s));
+    };
+    back(layers_host->beauty, L.beauty, sizeof(float4) * n);
+    back(layers_host->position, L.position, sizeof(float4) * n);
+    back(layers_host->normal, L.normal, sizeof(float4) * n);
+    back(layers_host->texcoord, L.texcoord, sizeof(float4) * n);
+    back(layers_host->albedo, L.albedo, sizeof(float4) * n);
+    back(layers_host->depth, L.depth, sizeof(float) * n);
+    FR_CUDA_CHECK(cudaStreamSynchronize(s));
+  });
+}
+
+int fr_scale_layers(fr_renderer* r, const fr_layers* layers_dev, float scale)
+{
+  return guarded([&] { r->renderer.scale_layers(make_layers(layers_dev), scale); });
+}
+
+int fr_get_statistics(fr_renderer* r, uint64_t* out5)
+{
+  return guarded([&] {
+    const RenderStatistics s = r->renderer.get_statistics();
+    out5[0] = s.paths;
+    out5[1] = s.rays_radiance;
+    out5[2] = s.rays_shadow;
+    out5[3] = s.rays_light;
+    out5[4] = s.kernel_launches;
+  });
+}
+int fr_reset_statistics(fr_renderer* r)
+{
+  return guarded([&] { r->renderer.reset_statistics(); });
+}
+uint64_t fr_get_stream(fr_renderer* r) { return reinterpret_cast<uint64_t>(r->renderer.get_stream()); }
+
+int fr_post_process(const void* beauty_in_dev, void* high_luminance_dev, void* temp_dev, int width, int height,
+                    const fr_post_process_params* p, void* beauty_out_dev)
+{
+  return guarded([&] {
+    PostProcessParams pp;
+    pp.use_bloom = p->use_bloom != 0;
+    pp.bloom_threshold = p->bloom_threshold;
+    pp.bloom_sigma = p->bloom_sigma;
+    pp.ISO = p->ISO;
+    pp.chromatic_aberration = p->chromatic_aberration;
+    post_process_kernel_launch(static_cast<const float4*>(beauty_in_dev), static_cast<float4*>(high_luminance_dev),
+                               static_cast<float4*>(temp_dev), width, height, pp,
+                               static_cast<float4*>(beauty_out_dev));
+    FR_CUDA_CHECK(cudaDeviceSynchronize());
+  });
+}
+
+int fr_tone_mapping(const void* beauty_in_dev, int width, int height, float ISO, float chromatic_aberration,
+                    void* beauty_out_dev)
+{
+  return guarded([&] {
+    tone_mapping_kernel_launch(static_cast<const float4*>(beauty_in_dev), width, height, ISO, chromatic_aberration,
+                               static_cast<float4*>(beauty_out_dev));
+    FR_CUDA_CHECK(cudaDeviceSynchronize());
+  });
+}
+
+void* fr_device_alloc(size_t bytes)
+{
+  void* p = nullptr;
+  if (guarded([&] { FR_CUDA_CHECK(cudaMalloc(&p, bytes)); }) != 0) return nullptr;
+  return p;
+}
+int fr_device_free(void* p)
+{
+  return guarded([&] { FR_CUDA_CHECK(cudaFree(p)); });
+}
+int fr_device_memset(void* p, int value, size_t bytes)
+{
+  return guarded([&] { FR_CUDA_CHECK(cudaMemset(p, value, bytes)); });
+}
+int fr_copy_to_device(void* dst_dev, const void* src_host, size_t bytes)
+{
+  return guarded([&] { FR_CUDA_CHECK(cudaMemcpy(dst_dev, src_host, bytes, cudaMemcpyHostToDevice)); });
+}
+int fr_copy_to_host(void* dst_host, const void* src_dev, size_t bytes)
+{
+  return guarded([&] { FR_CUDA_CHECK(cudaMemcpy(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost)); });
+}
+int fr_device_synchronize(void)
+{
+  return guarded([&] { FR_CUDA_CHECK(cudaDeviceSynchronize()); });
+}
+
+int fr_trace_closest(fr_renderer* r, const float* rays, uint32_t n, float tmin, float tmax, uint32_t* out_id,
+                     float* out_tuv, uint64_t* counters2)
+{
+  return guarded([&] {
+    Renderer::Impl* im = r->renderer.impl();
+    if (!im->accel_valid) im->build_accel();
+    FR_CUDA_CHECK(cudaStreamSynchronize(im->stream));
+    const frd::SceneView v = im->view(make_float3(0, 0, 0));
+    frd::trace_batch_closest(v, im->d_submesh_offsets.get(), rays, n, tmin, tmax, out_id, out_tuv,
+                             reinterpret_cast<unsigned long long*>(counters2));
+  });
+}
+
+int fr_primary_rays(fr_renderer* r, const float* camera_transform12, float fov, float F, float focus, uint32_t n_spp,
+                    float* out_rays)
+{
+  return guarded([&] {
+    Renderer::Impl* im = r->renderer.impl();
+    frd::WaveParams wp;
+    wp.film = frd::make_film_geom(im->width, im->height);
+    wp.n_samples = 1;
+    wp.sample_base = n_spp;
+    wp.max_depth = 1;
+    wp.seed = 1;
+    wp.camera = make_camera(camera_transform12, fov, F, focus);
+    frd::test_primary_rays(wp, out_rays);
+  });
+}
+
+int fr_sampler_sequence(uint32_t width, uint32_t height, uint32_t seed, uint32_t image_idx, uint32_t n_spp,
+                        const char* kinds, float* out)
+{
+  return guarded([&] {
+    uint32_t n_out = 0;
+    for (const char* k = kinds; *k; ++k) n_out += (*k == '1') ? 1u : 2u;
+    frd::test_sampler(width, height, seed, image_idx, n_spp, kinds, out, n_out);
+  });
+}
+
+int fr_bsdf_eval_sample(const float* in, uint32_t n, float* out)
+{
+  return guarded([&] { frd::test_bsdf(in, n, out); });
+}
+
+int fr_sky_radiance(fr_renderer* r, const float* dirs, uint32_t n, float* out)
+{
+  return guarded([&] {
+    const frd::SceneView v = r->renderer.impl()->view(make_float3(0, 0, 0));
+    frd::test_sky(v, dirs, n, out);
+  });
+}
+
+int fr_arhosek_cook(float turbidity, float albedo, float elevation, float* out30)
+{
+  return guarded([&] { arhosek_rgb_cook(turbidity, albedo, elevation, out30); });
+}
+
+int fr_camera_transform(const float* origin3, float* out12)
+{
+  return guarded([&] {
+    const Camera cam(make_float3(origin3[0], origin3[1], origin3[2]));
+    camera_rows(cam, out12);
+  });
+}
+
+int fr_camera_walk(const float* origin3, float d_phi, float d_theta, int movement, float dt, float* out12)
+{
+  return guarded([&] {
+    Camera cam(make_float3(origin3[0], origin3[1], origin3[2]));
+    cam.lookAround(d_phi, d_theta);
+    cam.move(static_cast<CameraMovement>(movement), dt);
+    camera_rows(cam, out12);
+  });
+}
+
+}  // extern "C"

@@ -1,0 +1,92 @@
+// Error handling and a minimal owning device buffer for the core's internals.
+// Error behaviour follows the reference (cwl/util.h:11-56): every failed CUDA
+// call becomes a std::runtime_error carrying the call text and file:line.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstddef>
+#include <sstream>
+#include <stdexcept>
+#include <utility>
+#include <vector>
+
+#define FR_CUDA_CHECK(call)                                                          \
+  do {                                                                               \
+    const cudaError_t fr_err_ = (call);                                              \
+    if (fr_err_ != cudaSuccess) {                                                    \
+      std::stringstream fr_ss_;                                                      \
+      fr_ss_ << "CUDA call (" << #call << ") failed with error: '"                   \
+             << cudaGetErrorString(fr_err_) << "' (" << __FILE__ << ":" << __LINE__ \
+             << ")";                                                                 \
+      throw std::runtime_error(fr_ss_.str());                                        \
+    }                                                                                \
+  } while (0)
+
+#define FR_CUDA_LAUNCH_CHECK() FR_CUDA_CHECK(cudaGetLastError())
+
+namespace frd
+{
+
+template <typename T>
+class DevBuf
+{
+ public:
+  DevBuf() = default;
+  explicit DevBuf(size_t n) { alloc(n); }
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  DevBuf(DevBuf&& o) noexcept : p_(o.p_), n_(o.n_)
+  {
+    o.p_ = nullptr;
+    o.n_ = 0;
+  }
+  DevBuf& operator=(DevBuf&& o) noexcept
+  {
+    if (this != &o) {
+      release();
+      p_ = o.p_;
+      n_ = o.n_;
+      o.p_ = nullptr;
+      o.n_ = 0;
+    }
+    return *this;
+  }
+  ~DevBuf() { release(); }
+
+  void alloc(size_t n)
+  {
+    release();
+    n_ = n;
+    if (n) FR_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&p_), n * sizeof(T)));
+  }
+  // grow-only (contents are NOT preserved)
+  void reserve(size_t n)
+  {
+    if (n > n_) alloc(n);
+  }
+  void release()
+  {
+    if (p_) cudaFree(p_);
+    p_ = nullptr;
+    n_ = 0;
+  }
+  void upload(const T* host, size_t n, cudaStream_t s = 0)
+  {
+    reserve(n);
+    if (n) FR_CUDA_CHECK(cudaMemcpyAsync(p_, host, n * sizeof(T), cudaMemcpyHostToDevice, s));
+  }
+  void upload(const std::vector<T>& v, cudaStream_t s = 0) { upload(v.data(), v.size(), s); }
+  void zero(cudaStream_t s = 0)
+  {
+    if (n_) FR_CUDA_CHECK(cudaMemsetAsync(p_, 0, n_ * sizeof(T), s));
+  }
+  T* get() const { return p_; }
+  size_t size() const { return n_; }
+  size_t bytes() const { return n_ * sizeof(T); }
+
+ private:
+  T* p_ = nullptr;
+  size_t n_ = 0;
+};
+
+}  // namespace frd

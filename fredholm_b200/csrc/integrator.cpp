@@ -1,0 +1,123 @@
+#include "integrator.h"
+
+#include <algorithm>
+
+namespace frd
+{
+
+void Integrator::ensure_capacity(size_t n_slots)
+{
+  if (m_ctl.size() == 0) {
+    m_ctl.alloc(1);
+    m_ctl.zero(m_stream);
+  }
+  if (n_slots <= m_capacity) return;
+  // buffers are in use by work already queued on the stream
+  FR_CUDA_CHECK(cudaStreamSynchronize(m_stream));
+  m_ray_o.alloc(n_slots);
+  m_ray_d.alloc(n_slots);
+  m_hit.alloc(n_slots);
+  m_thr.alloc(n_slots);
+  m_L.alloc(n_slots);
+  m_aov0.alloc(n_slots);
+  m_aov1.alloc(n_slots);
+  m_aov2.alloc(n_slots);
+  m_queue[0].alloc(n_slots);
+  m_queue[1].alloc(n_slots);
+  for (auto& s : m_shadow) s.alloc(n_slots);
+  m_light.alloc(n_slots);
+  m_capacity = n_slots;
+  m_state_bytes = n_slots * (8 * sizeof(float4) + 2 * sizeof(uint32_t) + 3 * sizeof(ShadowRay) + sizeof(LightRay));
+}
+
+void Integrator::render(const SceneView& scene, const fredholm::CameraParams& camera, uint32_t width,
+                        uint32_t height, const fredholm::RenderLayer& layers, uint32_t sample_base,
+                        uint32_t n_samples, uint32_t max_depth, uint32_t seed, int film_mode)
+{
+  if (width == 0 || height == 0 || n_samples == 0) return;
+  const FilmGeom film = make_film_geom(width, height);
+  const uint32_t per_wave =
+      (uint32_t)std::max<size_t>(1, std::min<size_t>(n_samples, m_max_wave_paths / film.slots_per_sample));
+  ensure_capacity((size_t)per_wave * film.slots_per_sample);
+
+  WaveBuffers wb;
+  wb.ray_o = m_ray_o.get();
+  wb.ray_d = m_ray_d.get();
+  wb.hit = m_hit.get();
+  wb.thr = m_thr.get();
+  wb.L = m_L.get();
+  wb.aov0 = m_aov0.get();
+  wb.aov1 = m_aov1.get();
+  wb.aov2 = m_aov2.get();
+  wb.queue[0] = m_queue[0].get();
+  wb.queue[1] = m_queue[1].get();
+  for (int k = 0; k < 3; ++k) wb.shadow[k] = m_shadow[k].get();
+  wb.light = m_light.get();
+  wb.ctl = m_ctl.get();
+
+  for (uint32_t done = 0; done < n_samples; done += per_wave) {
+    WaveParams wp;
+    wp.film = film;
+    wp.n_samples = std::min(per_wave, n_samples - done);
+    wp.sample_base = sample_base + done;
+    wp.max_depth = max_depth;
+    wp.seed = seed;
+    wp.camera = camera;
+
+    launch_wave_begin(m_stream, wb, (unsigned long long)wp.n_samples * width * height);
+    launch_generate(m_stream, wp, wb);
+    m_launches += 2;
+    for (uint32_t depth = 0; depth < max_depth; ++depth) {
+      launch_trace_closest(m_stream, scene, wb, depth);
+      launch_shade(m_stream, wp, scene, wb, depth);
+      m_launches += 2;
+      if (scene.has_dir_light) {
+        launch_trace_shadow(m_stream, scene, wb, 0);
+        m_launches++;
+      }
+      launch_trace_shadow(m_stream, scene, wb, 1);
+      m_launches++;
+      if (scene.n_lights > 0) {
+        launch_trace_shadow(m_stream, scene, wb, 2);
+        m_launches++;
+      }
+      launch_trace_light(m_stream, scene, wb);
+      launch_advance(m_stream, wb);
+      m_launches += 2;
+    }
+    launch_film(m_stream, wp, wb, layers, film_mode);
+    m_launches++;
+  }
+}
+
+void Integrator::scale_layers(const fredholm::RenderLayer& layers, uint32_t n_pixels, float scale)
+{
+  launch_scale_layers(m_stream, layers, n_pixels, scale);
+  m_launches++;
+}
+
+RenderStats Integrator::stats()
+{
+  RenderStats s;
+  s.launches = m_launches;
+  if (m_ctl.size() == 0) return s;
+  WaveControl h;
+  FR_CUDA_CHECK(cudaStreamSynchronize(m_stream));
+  FR_CUDA_CHECK(cudaMemcpy(&h, m_ctl.get(), sizeof(h), cudaMemcpyDeviceToHost));
+  s.paths = h.paths;
+  s.rays_closest = h.rays_closest;
+  s.rays_shadow = h.rays_shadow;
+  s.rays_light = h.rays_light;
+  return s;
+}
+
+void Integrator::reset_stats()
+{
+  m_launches = 0;
+  if (m_ctl.size()) {
+    FR_CUDA_CHECK(cudaStreamSynchronize(m_stream));
+    m_ctl.zero(m_stream);
+  }
+}
+
+}  // namespace frd

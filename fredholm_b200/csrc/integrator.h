@@ -1,0 +1,61 @@
+// Host driver of the wavefront integrator: owns the per-path state and the ray
+// queues in HBM and sequences the stages of one render call
+// (replaces the single optixLaunch of Renderer::render, renderer.h:730-733).
+#pragma once
+#include <cstdint>
+
+#include "cuda_util.h"
+#include "wavefront.h"
+#include "wavefront_kernels.h"
+
+namespace frd
+{
+
+struct RenderStats {
+  unsigned long long paths = 0;         // camera samples started
+  unsigned long long rays_closest = 0;  // radiance rays traced
+  unsigned long long rays_shadow = 0;   // visibility rays traced
+  unsigned long long rays_light = 0;    // MIS rays traced
+  unsigned long long launches = 0;      // kernels launched by the integrator
+};
+
+class Integrator
+{
+ public:
+  explicit Integrator(cudaStream_t stream) : m_stream(stream) {}
+
+  // paths kept in flight per wave; rounded down to whole samples (at least one)
+  void set_max_wave_paths(size_t n) { m_max_wave_paths = n; }
+  size_t max_wave_paths() const { return m_max_wave_paths; }
+
+  // Renders samples [sample_base, sample_base + n_samples) of every pixel into
+  // `layers` (device pointers).  Asynchronous on the stream.
+  void render(const SceneView& scene, const fredholm::CameraParams& camera, uint32_t width, uint32_t height,
+              const fredholm::RenderLayer& layers, uint32_t sample_base, uint32_t n_samples, uint32_t max_depth,
+              uint32_t seed, int film_mode);
+
+  void scale_layers(const fredholm::RenderLayer& layers, uint32_t n_pixels, float scale);
+
+  // blocks until the stream is idle, then reads the device counters
+  RenderStats stats();
+  void reset_stats();
+
+  size_t state_bytes() const { return m_state_bytes; }
+
+ private:
+  void ensure_capacity(size_t n_slots);
+
+  cudaStream_t m_stream;
+  size_t m_max_wave_paths = size_t(1) << 23;  // 8 Mi paths
+  size_t m_capacity = 0;
+  size_t m_state_bytes = 0;
+  unsigned long long m_launches = 0;
+
+  DevBuf<float4> m_ray_o, m_ray_d, m_hit, m_thr, m_L, m_aov0, m_aov1, m_aov2;
+  DevBuf<uint32_t> m_queue[2];
+  DevBuf<ShadowRay> m_shadow[3];
+  DevBuf<LightRay> m_light;
+  DevBuf<WaveControl> m_ctl;
+};
+
+}  // namespace frd

@@ -1,0 +1,239 @@
+// Post-process kernels: bloom (luminance threshold + 33x33 Gaussian), chromatic
+// aberration, EV100 exposure, Uchimura tone curve, sRGB encode.
+//
+// Behavioural spec: fredholm/kernels/src/post-process.cu:5-153 and
+// kernels/post-process.h:12-118 of the reference, including its launch-grid quirk:
+// the reference launches (max(W/16,1), max(H/16,1)) blocks of 16x16 threads with
+// INTEGER division, so pixels with x >= 16*(W/16) or y >= 16*(H/16) are never
+// written (1080 rows -> the last 8 keep their previous content).  `covered()`
+// reproduces that region.
+//
+// B200 design: the reference's bloom is a brute-force 1089-tap gather per pixel.
+// The kernel exp(-(u^2+v^2)/(2 sigma)) with per-axis edge clamping is separable, so
+// it runs as a horizontal and a vertical 33-tap pass over shared-memory tiles
+// (exact up to fp32 re-association).  The intermediate image lives in an internal
+// scratch buffer that stays L2-resident at 1080p (33 MB of the 126 MB L2).
+#include "kernels/post-process.h"
+
+#include <cmath>
+
+#include "cuda_util.h"
+#include "vecmath.cuh"
+
+namespace
+{
+
+using namespace frd;
+
+constexpr int kRadius = 16;  // K in bloom_kernel_1 (post-process.cu:88)
+
+__device__ __forceinline__ bool covered(int x, int y, int width, int height)
+{
+  const int cw = max(width / 16, 1) * 16, ch = max(height / 16, 1) * 16;
+  return x < width && y < height && x < cw && y < ch;
+}
+
+__device__ __forceinline__ float4 f4_scale_add(const float4& acc, float w, const float4& v)
+{
+  return make_float4(acc.x + w * v.x, acc.y + w * v.y, acc.z + w * v.z, acc.w + w * v.w);
+}
+
+// pass 1: threshold + horizontal blur.  One block = one 128-pixel row segment.
+// tmp[x,y] = sum_u h(u) * bright(clamp(x+u), y); also materialises the
+// high-luminance image for the covered region (bloom_kernel_0).
+constexpr int kRowSeg = 128;
+__global__ void __launch_bounds__(kRowSeg) k_bloom_h(const float4* __restrict__ beauty_in,
+                                                      float4* __restrict__ high, int width, int height,
+                                                      float threshold, float sigma, float4* __restrict__ tmp)
+{
+  __shared__ float4 s_row[kRowSeg + 2 * kRadius];
+  __shared__ float s_w[2 * kRadius + 1];
+  const int y = blockIdx.y;
+  const int x0 = blockIdx.x * kRowSeg;
+  for (int i = threadIdx.x; i < kRowSeg + 2 * kRadius; i += kRowSeg) {
+    const int xs = min(max(x0 + i - kRadius, 0), width - 1);
+    float4 v;
+    if (covered(xs, y, width, height)) {
+      const float4 b = beauty_in[xs + width * y];
+      v = luminance(f3(b)) > threshold ? b : make_float4(0.f, 0.f, 0.f, 0.f);
+      // each covered pixel is written by the block that owns it
+      if (i >= kRadius && i < kRadius + kRowSeg && x0 + i - kRadius < width) high[xs + width * y] = v;
+    } else {
+      v = high[xs + width * y];  // the reference blurs whatever the buffer holds there
+    }
+    s_row[i] = v;
+  }
+  if (threadIdx.x <= 2 * kRadius) {
+    const float u = (float)((int)threadIdx.x - kRadius);
+    s_w[threadIdx.x] = expf(-(u * u) / (2.0f * sigma));
+  }
+  __syncthreads();
+  const int x = x0 + threadIdx.x;
+  if (x >= width) return;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int u = 0; u <= 2 * kRadius; ++u) acc = f4_scale_add(acc, s_w[u], s_row[threadIdx.x + u]);
+  tmp[x + width * y] = acc;
+}
+
+// pass 2: vertical blur + normalisation + add to the input (bloom_kernel_1).
+constexpr int kTile = 32;
+__global__ void __launch_bounds__(kTile* 8) k_bloom_v(const float4* __restrict__ beauty_in,
+                                                      const float4* __restrict__ tmp, int width, int height,
+                                                      float sigma, float4* __restrict__ beauty_out)
+{
+  __shared__ float4 s_col[kTile + 2 * kRadius][kTile];
+  __shared__ float s_w[2 * kRadius + 1];
+  const int x = blockIdx.x * kTile + threadIdx.x;
+  const int y0 = blockIdx.y * kTile;
+  for (int r = threadIdx.y; r < kTile + 2 * kRadius; r += 8) {
+    const int ys = min(max(y0 + r - kRadius, 0), height - 1);
+    s_col[r][threadIdx.x] = x < width ? tmp[x + width * ys] : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const int tid = threadIdx.y * kTile + threadIdx.x;
+  if (tid <= 2 * kRadius) {
+    const float v = (float)(tid - kRadius);
+    s_w[tid] = expf(-(v * v) / (2.0f * sigma));
+  }
+  __syncthreads();
+  float w1 = 0.0f;
+#pragma unroll
+  for (int v = 0; v <= 2 * kRadius; ++v) w1 += s_w[v];
+  const float w_sum = w1 * w1;
+  for (int r = threadIdx.y; r < kTile; r += 8) {
+    const int y = y0 + r;
+    if (!covered(x, y, width, height)) continue;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int v = 0; v <= 2 * kRadius; ++v) acc = f4_scale_add(acc, s_w[v], s_col[r + v][threadIdx.x]);
+    const float4 b0 = beauty_in[x + width * y];
+    const float inv = 1.0f / w_sum;
+    beauty_out[x + width * y] =
+        make_float4(b0.x + acc.x * inv, b0.y + acc.y * inv, b0.z + acc.z * inv, b0.w + acc.w * inv);
+  }
+}
+
+__global__ void k_copy(const float4* __restrict__ in, int width, int height, float4* __restrict__ out)
+{
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (!covered(x, y, width, height)) return;
+  out[x + width * y] = in[x + width * y];
+}
+
+// ---- tone mapping ------------------------------------------------------------------------
+__device__ __forceinline__ float smoothstep01(float e0, float e1, float x)
+{
+  if (x < e0) return 0.0f;
+  if (x > e1) return 1.0f;
+  x = (x - e0) / (e1 - e0);
+  return x * x * (3.0f - 2.0f * x);
+}
+
+// Uchimura 2017 "HDR theory and practice", P=1 a=1 m=0.22 l=0.4 c=1.33 b=0
+__device__ __forceinline__ float uchimura1(float x)
+{
+  const float P = 1.0f, a = 1.0f, m = 0.22f, l = 0.4f, c = 1.33f, b = 0.0f;
+  const float l0 = ((P - m) * l) / a;
+  const float S0 = m + l0;
+  const float S1 = m + a * l0;
+  const float C2 = (a * P) / (P - S1);
+  const float CP = -C2 / P;
+  const float w0 = 1.0f - smoothstep01(0.0f, m, x);
+  const float w2 = (x < m + l0) ? 0.0f : 1.0f;
+  const float w1 = 1.0f - w0 - w2;
+  const float T = m * powf(x / m, c) + b;
+  const float S = P - (P - S1) * expf(CP * (x - S0));
+  const float L = m + a * (x - m);
+  return T * w0 + L * w1 + S * w2;
+}
+
+__device__ __forceinline__ float srgb_encode(float x)
+{
+  return x < 0.0031308 ? (float)(12.92 * x) : (float)(1.055 * powf(x, 1.0f / 2.4f) - 0.055);
+}
+
+// pixel index the reference derives from a (clamped) uv through float arithmetic:
+// int(u*W + W*(v*H)), each operation rounded separately (host-oracle semantics)
+__device__ __forceinline__ int uv_index(float u, float v, float wf, float hf)
+{
+  return (int)__fadd_rn(__fmul_rn(u, wf), __fmul_rn(wf, __fmul_rn(v, hf)));
+}
+
+__global__ void k_tone_map(const float4* __restrict__ beauty_in, int width, int height, float exposure,
+                           float chromatic_aberration, float4* __restrict__ beauty_out)
+{
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (!covered(x, y, width, height)) return;
+  const float wf = (float)width, hf = (float)height;
+  const float u = __fdiv_rn((float)x, wf), v = __fdiv_rn((float)y, hf);
+  const float inv = __fdiv_rn(1.0f, (float)(width * height));
+  const float dx = __fmul_rn(__fmul_rn(__fsub_rn(u, 0.5f), inv), chromatic_aberration);
+  const float dy = __fmul_rn(__fmul_rn(__fsub_rn(v, 0.5f), inv), chromatic_aberration);
+  int idx[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float k = (float)c;
+    const float uu = clampf(__fsub_rn(u, __fmul_rn(k, dx)), 0.0f, 1.0f);
+    const float vv = clampf(__fsub_rn(v, __fmul_rn(k, dy)), 0.0f, 1.0f);
+    idx[c] = uv_index(uu, vv, wf, hf);
+  }
+  float3 color = f3(beauty_in[idx[0]].x, beauty_in[idx[1]].y, beauty_in[idx[2]].z);
+  color *= exposure;
+  color = f3(uchimura1(color.x), uchimura1(color.y), uchimura1(color.z));
+  beauty_out[x + width * y] = make_float4(srgb_encode(color.x), srgb_encode(color.y), srgb_encode(color.z), 1.0f);
+}
+
+// EV100(aperture 1, shutter 1, ISO) -> exposure (post-process.h:103-118)
+float exposure_from_iso(float ISO)
+{
+  const float ev100 = log2f((float)(1.0f * 1.0f / 1.0f * 100.0 / ISO));
+  const float max_luminance = (float)(1.2 * powf(2.0f, ev100));
+  return 1.0f / max_luminance;
+}
+
+frd::DevBuf<float4>& scratch(size_t n)
+{
+  static thread_local frd::DevBuf<float4> buf;
+  buf.reserve(n);
+  return buf;
+}
+
+void launch_tone_map(const float4* in, int width, int height, float ISO, float ca, float4* out)
+{
+  const dim3 block(32, 8);
+  const dim3 grid((width + 31) / 32, (height + 7) / 8);
+  k_tone_map<<<grid, block>>>(in, width, height, exposure_from_iso(ISO), ca, out);
+  FR_CUDA_LAUNCH_CHECK();
+}
+
+}  // namespace
+
+void post_process_kernel_launch(const float4* beauty_in, float4* beauty_high_luminance, float4* beauty_temp,
+                                int width, int height, const PostProcessParams& params, float4* beauty_out)
+{
+  if (params.use_bloom) {
+    frd::DevBuf<float4>& tmp = scratch((size_t)width * height);
+    const dim3 grid_h((width + kRowSeg - 1) / kRowSeg, height);
+    k_bloom_h<<<grid_h, kRowSeg>>>(beauty_in, beauty_high_luminance, width, height, params.bloom_threshold,
+                                   params.bloom_sigma, tmp.get());
+    FR_CUDA_LAUNCH_CHECK();
+    const dim3 block_v(kTile, 8);
+    const dim3 grid_v((width + kTile - 1) / kTile, (height + kTile - 1) / kTile);
+    k_bloom_v<<<grid_v, block_v>>>(beauty_in, tmp.get(), width, height, params.bloom_sigma, beauty_temp);
+    FR_CUDA_LAUNCH_CHECK();
+  } else {
+    const dim3 block(32, 8);
+    const dim3 grid((width + 31) / 32, (height + 7) / 8);
+    k_copy<<<grid, block>>>(beauty_in, width, height, beauty_temp);
+    FR_CUDA_LAUNCH_CHECK();
+  }
+  launch_tone_map(beauty_temp, width, height, params.ISO, params.chromatic_aberration, beauty_out);
+}
+
+void tone_mapping_kernel_launch(const float4* beauty_in, int width, int height, float ISO,
+                                float chromatic_aberration, float4* beauty_out)
+{
+  launch_tone_map(beauty_in, width, height, ISO, chromatic_aberration, beauty_out);
+}

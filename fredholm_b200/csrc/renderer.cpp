@@ -1,0 +1,424 @@
+// Host side of fredholm::Renderer: scene upload, light extraction, sky setup,
+// acceleration-structure build and the render call.
+//
+// Upload logic follows Renderer::load_scene of the reference (renderer.h:354-432):
+// flat arrays -> device buffers, one texture header per texture, the area-light
+// list = every face whose material has emission (renderer.h:388-402), one
+// object-to-world / world-to-object 3x4 pair per sub-mesh (renderer.h:404-421).
+#include "fredholm/renderer.h"
+
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <stdexcept>
+#include <vector>
+
+#include "renderer_impl.h"
+
+namespace fredholm
+{
+
+namespace
+{
+
+// ---- Hosek-Wilkie RGB datasets (data: tables/hosek_rgb_*.inc) ----
+const float kHosekConfig[3][1080] = {{
+#include "tables/hosek_rgb_config_r.inc"
+                                     },
+                                     {
+#include "tables/hosek_rgb_config_g.inc"
+                                     },
+                                     {
+#include "tables/hosek_rgb_config_b.inc"
+                                     }};
+const float kHosekRadiance[3][120] = {{
+#include "tables/hosek_rgb_radiance_r.inc"
+                                      },
+                                      {
+#include "tables/hosek_rgb_radiance_g.inc"
+                                      },
+                                      {
+#include "tables/hosek_rgb_radiance_b.inc"
+                                      }};
+
+// quintic Bezier weights in the solar-elevation parameter
+void elevation_weights(float elevation, float w[6])
+{
+  const float x = std::pow(elevation / (3.141592653589793f / 2.0f), (1.0f / 3.0f));
+  w[0] = std::pow(1.0f - x, 5.0f);
+  w[1] = 5.0f * std::pow(1.0f - x, 4.0f) * x;
+  w[2] = 10.0f * std::pow(1.0f - x, 3.0f) * std::pow(x, 2.0f);
+  w[3] = 10.0f * std::pow(1.0f - x, 2.0f) * std::pow(x, 3.0f);
+  w[4] = 5.0f * (1.0f - x) * std::pow(x, 4.0f);
+  w[5] = std::pow(x, 5.0f);
+}
+
+Matrix3x4 rows_of(const mat4& m)
+{
+  return make_mat3x4(make_float4(m[0][0], m[1][0], m[2][0], m[3][0]), make_float4(m[0][1], m[1][1], m[2][1], m[3][1]),
+                     make_float4(m[0][2], m[1][2], m[2][2], m[3][2]));
+}
+
+float3 normalized(const float3& v)
+{
+  const float inv = 1.0f / std::sqrt(v.x * v.x + v.y * v.y + v.z * v.z);
+  return make_float3(v.x * inv, v.y * inv, v.z * inv);
+}
+
+}  // namespace
+
+// Interpolation of the Hosek coefficient tables: bilinear in (albedo, turbidity),
+// quintic Bezier in cbrt(elevation / 90deg)  (reference arhosek.h:145-323).
+void arhosek_rgb_cook(float turbidity, float albedo, float elevation, float out30[30])
+{
+  const int it = static_cast<int>(turbidity);
+  const float rem = turbidity - static_cast<float>(it);
+  float w[6];
+  elevation_weights(elevation, w);
+  for (int ch = 0; ch < 3; ++ch) {
+    // (albedo index, turbidity slot, blend factor) in the reference's summation order
+    const struct {
+      int alb, turb;
+      float k;
+    } corners[4] = {{0, it - 1, (1.0f - albedo) * (1.0f - rem)},
+                    {1, it - 1, albedo * (1.0f - rem)},
+                    {0, it, (1.0f - albedo) * rem},
+                    {1, it, albedo * rem}};
+    const int n_corners = it == 10 ? 2 : 4;
+    for (int i = 0; i < 9; ++i) {
+      float acc = 0.0f;
+      for (int c = 0; c < n_corners; ++c) {
+        const float* e = kHosekConfig[ch] + 9 * 6 * 10 * corners[c].alb + 9 * 6 * corners[c].turb;
+        const float bez = w[0] * e[i] + w[1] * e[i + 9] + w[2] * e[i + 18] + w[3] * e[i + 27] + w[4] * e[i + 36] +
+                          w[5] * e[i + 45];
+        acc = c == 0 ? corners[c].k * bez : acc + corners[c].k * bez;
+      }
+      out30[9 * ch + i] = acc;
+    }
+    float acc = 0.0f;
+    for (int c = 0; c < n_corners; ++c) {
+      const float* e = kHosekRadiance[ch] + 6 * 10 * corners[c].alb + 6 * corners[c].turb;
+      const float bez = w[0] * e[0] + w[1] * e[1] + w[2] * e[2] + w[3] * e[3] + w[4] * e[4] + w[5] * e[5];
+      acc = c == 0 ? corners[c].k * bez : acc + corners[c].k * bez;
+    }
+    out30[27 + ch] = acc;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+void Renderer::Impl::upload_transforms()
+{
+  std::vector<Matrix3x4> o2w(scene.m_transforms.size()), w2o(scene.m_transforms.size());
+  for (size_t i = 0; i < scene.m_transforms.size(); ++i) {
+    o2w[i] = rows_of(scene.m_transforms[i]);
+    w2o[i] = rows_of(inverse(scene.m_transforms[i]));
+  }
+  d_o2w.upload(o2w, stream);
+  d_w2o.upload(w2o, stream);
+  FR_CUDA_CHECK(cudaStreamSynchronize(stream));
+  accel_valid = false;
+}
+
+void Renderer::Impl::upload_scene()
+{
+  const Scene& s = scene;
+  FR_CUDA_CHECK(cudaStreamSynchronize(stream));
+  d_vertices.upload(s.m_vertices, stream);
+  d_normals.upload(s.m_normals, stream);
+  d_texcoords.upload(s.m_texcoords, stream);
+  d_indices.upload(s.m_indices, stream);
+  d_material_ids.upload(s.m_material_ids, stream);
+  d_materials.upload(s.m_materials, stream);
+  d_submesh_offsets.upload(s.m_submesh_offsets, stream);
+
+  // face -> sub-mesh (== instance, == transform) and the alpha-test flag
+  std::vector<uint32_t> face_submesh(s.m_indices.size(), 0), face_flags(s.m_indices.size(), 0);
+  for (size_t sm = 0; sm < s.m_submesh_offsets.size(); ++sm)
+    for (uint32_t f = 0; f < s.m_submesh_n_faces[sm]; ++f) face_submesh[s.m_submesh_offsets[sm] + f] = (uint32_t)sm;
+  for (size_t f = 0; f < s.m_indices.size(); ++f) {
+    const uint32_t mid = s.m_material_ids[f];
+    if (mid >= s.m_materials.size()) throw std::runtime_error("invalid scene: face without a valid material");
+    const Material& m = s.m_materials[mid];
+    face_flags[f] = (m.base_color_texture_id >= 0 || m.alpha_texture_id >= 0) ? 1u : 0u;
+  }
+  d_face_submesh.upload(face_submesh, stream);
+  d_face_flags.upload(face_flags, stream);
+
+  // textures
+  d_texture_data.clear();
+  d_texture_data.resize(s.m_textures.size());
+  std::vector<frd::TexView> views(s.m_textures.size());
+  for (size_t i = 0; i < s.m_textures.size(); ++i) {
+    const Texture& t = s.m_textures[i];
+    d_texture_data[i].upload(t.m_data, stream);
+    views[i].texels = d_texture_data[i].get();
+    views[i].width = t.m_width;
+    views[i].height = t.m_height;
+    views[i].srgb = t.m_texture_type == TextureType::COLOR ? 1u : 0u;
+    views[i].pad_ = 0;
+  }
+  if (!views.empty()) d_textures.upload(views, stream);
+  if (d_srgb_lut.size() == 0) {
+    std::vector<float> lut(256);
+    for (int c = 0; c < 256; ++c) {
+      const double v = c / 255.0;
+      lut[c] = static_cast<float>(v <= 0.04045 ? v / 12.92 : std::pow((v + 0.055) / 1.055, 2.4));
+    }
+    d_srgb_lut.upload(lut, stream);
+  }
+
+  // emissive faces become area lights
+  std::vector<AreaLight> lights;
+  for (size_t f = 0; f < s.m_material_ids.size(); ++f) {
+    const Material& m = s.m_materials[s.m_material_ids[f]];
+    if (m.emission_color.x > 0 || m.emission_color.y > 0 || m.emission_color.z > 0 || m.emission_texture_id != -1) {
+      AreaLight l;
+      l.indices = s.m_indices[f];
+      l.material_id = s.m_material_ids[f];
+      l.instance_idx = s.m_instance_ids[f];
+      lights.push_back(l);
+    }
+  }
+  n_lights = (uint32_t)lights.size();
+  if (n_lights) d_lights.upload(lights, stream);
+  upload_transforms();
+}
+
+void Renderer::Impl::build_accel()
+{
+  cudaEvent_t e0, e1;
+  FR_CUDA_CHECK(cudaEventCreate(&e0));
+  FR_CUDA_CHECK(cudaEventCreate(&e1));
+  FR_CUDA_CHECK(cudaEventRecord(e0, stream));
+  frd::build_bvh(stream, d_vertices.get(), d_indices.get(), d_face_submesh.get(), d_face_flags.get(), d_o2w.get(),
+                 (uint32_t)scene.m_indices.size(), bvh);
+  FR_CUDA_CHECK(cudaEventRecord(e1, stream));
+  FR_CUDA_CHECK(cudaEventSynchronize(e1));
+  FR_CUDA_CHECK(cudaEventElapsedTime(&accel_info.build_ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  accel_info.n_faces = bvh.n_faces;
+  accel_info.n_nodes = bvh.n_nodes;
+  accel_info.depth = bvh.depth;
+  accel_info.bytes = bvh.nodes.bytes() + bvh.tris.bytes();
+  accel_valid = true;
+}
+
+frd::SceneView Renderer::Impl::view(const float3& bg_color) const
+{
+  frd::SceneView v{};
+  v.vertices = d_vertices.get();
+  v.normals = d_normals.get();
+  v.texcoords = d_texcoords.get();
+  v.indices = d_indices.get();
+  v.material_ids = d_material_ids.get();
+  v.face_submesh = d_face_submesh.get();
+  v.materials = d_materials.get();
+  v.textures = d_textures.get();
+  v.srgb_lut = d_srgb_lut.get();
+  v.o2w = d_o2w.get();
+  v.w2o = d_w2o.get();
+  v.lights = d_lights.get();
+  v.n_lights = n_lights;
+  v.bvh = bvh.view();
+  v.has_dir_light = has_dir_light ? 1 : 0;
+  v.dir_light = dir_light;
+  if (has_dir_light) {
+    // disk of directions at distance 1e9 (pt.cu:324-342)
+    const float3 n = dir_light.dir;
+    const float sign = std::copysign(1.0f, n.z);
+    const float a = -1.0f / (sign + n.z);
+    const float b = n.x * n.y * a;
+    v.dir_t = make_float3(1.0f + sign * n.x * n.x * a, sign * b, -sign * n.x);
+    v.dir_b = make_float3(b, sign + n.y * n.y * a, -n.y);
+    const float half_angle_rad = (0.5f * dir_light.angle) * 3.14159265358979323846f / 180.0f;
+    v.dir_disk_radius = 1e9f * std::tan(half_angle_rad);
+  }
+  v.sky_mode = d_ibl.size() ? frd::SKY_IBL : (has_hosek ? frd::SKY_HOSEK : frd::SKY_CONSTANT);
+  v.sky_intensity = sky_intensity;
+  v.bg_color = bg_color;
+  v.sun_dir = sun_direction;
+  v.hosek = hosek;
+  v.ibl_texels = d_ibl.get();
+  v.ibl_width = ibl_w;
+  v.ibl_height = ibl_h;
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------
+Renderer::Renderer(int cuda_device) : m_impl(new Impl())
+{
+  m_impl->device = cuda_device;
+  FR_CUDA_CHECK(cudaSetDevice(cuda_device));
+  FR_CUDA_CHECK(cudaFree(nullptr));
+  FR_CUDA_CHECK(cudaStreamCreate(&m_impl->stream));
+  m_impl->integrator = std::make_unique<frd::Integrator>(m_impl->stream);
+}
+
+Renderer::~Renderer() noexcept(false)
+{
+  if (m_impl && m_impl->stream) {
+    cudaStreamSynchronize(m_impl->stream);
+    m_impl->integrator.reset();
+    cudaStreamDestroy(m_impl->stream);
+    m_impl->stream = nullptr;
+  }
+}
+
+void Renderer::create_module(const std::filesystem::path&) {}
+void Renderer::create_program_group() {}
+void Renderer::create_pipeline() {}
+void Renderer::create_sbt() {}
+
+void Renderer::load_scene(const std::filesystem::path& filepath, bool clear)
+{
+  FR_CUDA_CHECK(cudaSetDevice(m_impl->device));
+  m_impl->scene.load_model(filepath, clear);
+  if (!m_impl->scene.is_valid()) throw std::runtime_error("invalid scene");
+  m_impl->upload_scene();
+}
+
+void Renderer::set_scene(const Scene& scene)
+{
+  FR_CUDA_CHECK(cudaSetDevice(m_impl->device));
+  m_impl->scene = scene;
+  if (!m_impl->scene.is_valid()) throw std::runtime_error("invalid scene");
+  m_impl->upload_scene();
+}
+
+const Scene& Renderer::get_scene() const { return m_impl->scene; }
+
+void Renderer::build_gas()
+{
+  FR_CUDA_CHECK(cudaSetDevice(m_impl->device));
+  m_impl->build_accel();
+}
+
+void Renderer::build_ias()
+{
+  // instances are flattened into the one world-space tree; nothing to do unless
+  // the tree is stale (transforms changed)
+  if (!m_impl->accel_valid) build_gas();
+}
+
+void Renderer::set_time(float time)
+{
+  FR_CUDA_CHECK(cudaSetDevice(m_impl->device));
+  m_impl->scene.update_animation(time);
+  m_impl->upload_transforms();
+  m_impl->build_accel();
+}
+
+void Renderer::set_directional_light(const float3& le, const float3& dir, float angle)
+{
+  m_impl->dir_light.le = le;
+  m_impl->dir_light.dir = normalized(dir);
+  m_impl->dir_light.angle = angle;
+  m_impl->sun_direction = normalized(dir);
+  m_impl->has_dir_light = true;
+}
+void Renderer::clear_directional_light() { m_impl->has_dir_light = false; }
+void Renderer::set_sky_intensity(float sky_intensity) { m_impl->sky_intensity = sky_intensity; }
+
+void Renderer::load_ibl(const std::filesystem::path& filepath)
+{
+  const FloatTexture ibl(filepath);
+  set_ibl(ibl.m_data.data(), ibl.m_width, ibl.m_height);
+}
+void Renderer::set_ibl(const float4* texels, uint32_t width, uint32_t height)
+{
+  FR_CUDA_CHECK(cudaSetDevice(m_impl->device));
+  FR_CUDA_CHECK(cudaStreamSynchronize(m_impl->stream));
+  m_impl->d_ibl.alloc((size_t)width * height);
+  FR_CUDA_CHECK(cudaMemcpy(m_impl->d_ibl.get(), texels, sizeof(float4) * width * height, cudaMemcpyHostToDevice));
+  m_impl->ibl_w = width;
+  m_impl->ibl_h = height;
+}
+void Renderer::clear_ibl()
+{
+  FR_CUDA_CHECK(cudaStreamSynchronize(m_impl->stream));
+  m_impl->d_ibl.release();
+  m_impl->ibl_w = m_impl->ibl_h = 0;
+}
+
+void Renderer::load_arhosek_sky(float turbidity, float albedo)
+{
+  // solar elevation from the current sun direction (renderer.h:592-603)
+  const float cy = std::fmax(-1.0f, std::fmin(m_impl->sun_direction.y, 1.0f));
+  float elevation = std::acos(cy);
+  elevation = 0.5f * M_PI - elevation;
+  float cooked[30];
+  arhosek_rgb_cook(turbidity, albedo, elevation, cooked);
+  for (int c = 0; c < 3; ++c) {
+    for (int i = 0; i < 9; ++i) m_impl->hosek.cfg[c][i] = cooked[9 * c + i];
+    m_impl->hosek.rad[c] = cooked[27 + c];
+  }
+  m_impl->has_hosek = true;
+}
+void Renderer::clear_arhosek_sky() { m_impl->has_hosek = false; }
+
+void Renderer::set_resolution(uint32_t width, uint32_t height)
+{
+  m_impl->width = width;
+  m_impl->height = height;
+  init_render_states();
+}
+void Renderer::init_render_states() { m_impl->sample_count = 0; }
+
+void Renderer::render(const Camera& camera, const float3& bg_color, const RenderLayer& render_layer,
+                      uint32_t n_samples, uint32_t max_depth)
+{
+  CameraParams cp;
+  // a camera node of the scene overrides the application camera (renderer.h:671-685)
+  cp.transform = rows_of(m_impl->scene.m_has_camera_transform ? m_impl->scene.m_camera_transform : camera.m_transform);
+  cp.fov = camera.m_fov;
+  cp.F = camera.m_F;
+  cp.focus = camera.m_focus;
+  render(cp, bg_color, render_layer, n_samples, max_depth);
+}
+
+void Renderer::render(const CameraParams& camera, const float3& bg_color, const RenderLayer& render_layer,
+                      uint32_t n_samples, uint32_t max_depth)
+{
+  FR_CUDA_CHECK(cudaSetDevice(m_impl->device));
+  if (!m_impl->accel_valid) m_impl->build_accel();
+  const frd::SceneView view = m_impl->view(bg_color);
+  m_impl->integrator->render(view, camera, m_impl->width, m_impl->height, render_layer, m_impl->sample_count,
+                             n_samples, max_depth, /*seed=*/1u,
+                             m_impl->film_mode == FilmMode::MEAN ? frd::FILM_MEAN : frd::FILM_SUM);
+  m_impl->sample_count += n_samples;
+}
+
+void Renderer::wait_for_completion()
+{
+  FR_CUDA_CHECK(cudaSetDevice(m_impl->device));
+  FR_CUDA_CHECK(cudaDeviceSynchronize());
+  FR_CUDA_CHECK(cudaGetLastError());
+}
+
+void Renderer::set_sample_offset(uint32_t first_sample) { m_impl->sample_count = first_sample; }
+uint32_t Renderer::get_sample_count() const { return m_impl->sample_count; }
+void Renderer::set_film_mode(FilmMode mode) { m_impl->film_mode = mode; }
+void Renderer::scale_layers(const RenderLayer& render_layer, float scale)
+{
+  m_impl->integrator->scale_layers(render_layer, m_impl->width * m_impl->height, scale);
+}
+void Renderer::set_max_wave_paths(size_t n_paths) { m_impl->integrator->set_max_wave_paths(n_paths); }
+
+RenderStatistics Renderer::get_statistics()
+{
+  const frd::RenderStats s = m_impl->integrator->stats();
+  RenderStatistics r;
+  r.paths = s.paths;
+  r.rays_radiance = s.rays_closest;
+  r.rays_shadow = s.rays_shadow;
+  r.rays_light = s.rays_light;
+  r.kernel_launches = s.launches;
+  return r;
+}
+void Renderer::reset_statistics() { m_impl->integrator->reset_stats(); }
+AccelInfo Renderer::get_accel_info() const { return m_impl->accel_info; }
+cudaStream_t Renderer::get_stream() const { return m_impl->stream; }
+int Renderer::get_device() const { return m_impl->device; }
+
+}  // namespace fredholm

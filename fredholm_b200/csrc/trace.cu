@@ -1,0 +1,229 @@
+// Traversal stages of the wavefront integrator: persistent-thread kernels that pull
+// rays from the HBM queues in warp-sized batches and walk the CWBVH (bvh.cuh).
+//
+//   k_trace_closest  radiance rays    (reference trace_radiance, pt.cu:82-94)
+//   k_trace_shadow   visibility rays  (trace_shadow + __miss__/__closesthit__shadow,
+//                                      pt.cu:96-109, 525-529, 946-950)
+//   k_trace_light    MIS rays         (trace_light + __closesthit__light / __miss__light,
+//                                      pt.cu:111-123, 531-543, 952-998) with the emitter
+//                                      record and MIS weight resolved in the epilogue
+// All three honour the reference's alpha cut-out (any-hit programs, pt.cu:545-678).
+#include "cuda_util.h"
+#include "queue.cuh"
+#include "surface.cuh"
+#include "wavefront.h"
+#include "wavefront_kernels.h"
+
+namespace frd
+{
+namespace
+{
+
+constexpr int kBlock = 128;
+
+// alpha cut-out: candidate is ignored if base-colour alpha or the alpha map is < 0.5
+struct AlphaTest {
+  const SceneView* sc;
+  FR_D bool operator()(uint32_t face, float u, float v) const
+  {
+    const fredholm::Material& m = sc->materials[sc->material_ids[face]];
+    const uint3 idx = sc->indices[face];
+    const float2 uv = bary2(sc->texcoords[idx.x], sc->texcoords[idx.y], sc->texcoords[idx.z], u, v);
+    const SceneTex tex{sc->textures, sc->srgb_lut};
+    bool accept = true;
+    if (m.base_color_texture_id >= 0 && tex.fetch(m.base_color_texture_id, uv).w < 0.5f) accept = false;
+    if (m.alpha_texture_id >= 0 && tex.fetch(m.alpha_texture_id, uv).x < 0.5f) accept = false;
+    return accept;
+  }
+};
+
+#define FR_DECLARE_STACK()                                  \
+  __shared__ uint2 s_stack[kSmemStack * kBlock];            \
+  TravStack st;                                             \
+  st.smem = s_stack + threadIdx.x;                          \
+  st.stride = kBlock;                                       \
+  st.sp = 0
+
+__global__ void __launch_bounds__(kBlock) k_trace_closest(SceneView sc, WaveBuffers wb, uint32_t depth)
+{
+  FR_DECLARE_STACK();
+  WaveControl* ctl = wb.ctl;
+  const uint32_t n = ctl->n[Q_CUR];
+  const uint32_t* q = wb.queue[depth & 1u];
+  const AlphaTest alpha{&sc};
+  uint32_t item;
+  while (fetch_batch(&ctl->cursor[0], n, item)) {
+    if (item >= n) continue;
+    const uint32_t slot = q[item];
+    const float4 o = wb.ray_o[slot], d = wb.ray_d[slot];
+    const HitRecord h = traverse<false, false>(sc.bvh, f3(o), f3(d), 0.0f, 1e9f, st, alpha, nullptr);
+    wb.hit[slot] = make_float4(h.t, h.u, h.v, __uint_as_float(h.face));
+  }
+}
+
+__global__ void __launch_bounds__(kBlock) k_trace_shadow(SceneView sc, WaveBuffers wb, int which)
+{
+  FR_DECLARE_STACK();
+  WaveControl* ctl = wb.ctl;
+  const uint32_t n = ctl->n[Q_SHADOW0 + which];
+  const float4* q = reinterpret_cast<const float4*>(wb.shadow[which]);
+  const AlphaTest alpha{&sc};
+  uint32_t item;
+  while (fetch_batch(&ctl->cursor[2 + which], n, item)) {
+    if (item >= n) continue;
+    const float4 r0 = q[3ull * item], r1 = q[3ull * item + 1], r2 = q[3ull * item + 2];
+    const HitRecord h =
+        traverse<true, false>(sc.bvh, f3(r0), f3(r1), 0.0f, r0.w, st, alpha, nullptr);
+    if (h.face == kNoHit) {
+      // one ray per path and kernel: plain read-modify-write, deterministic order
+      const uint32_t path = __float_as_uint(r1.w);
+      float4 L = wb.L[path];
+      L.x += r2.x;
+      L.y += r2.y;
+      L.z += r2.z;
+      wb.L[path] = L;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kBlock) k_trace_light(SceneView sc, WaveBuffers wb)
+{
+  FR_DECLARE_STACK();
+  WaveControl* ctl = wb.ctl;
+  const uint32_t n = ctl->n[Q_LIGHT];
+  const float4* q = reinterpret_cast<const float4*>(wb.light);
+  const AlphaTest alpha{&sc};
+  uint32_t item;
+  while (fetch_batch(&ctl->cursor[5], n, item)) {
+    if (item >= n) continue;
+    const float4 r0 = q[3ull * item], r1 = q[3ull * item + 1], r2 = q[3ull * item + 2];
+    const float3 o = f3(r0), d = f3(r1);
+    const HitRecord h = traverse<false, false>(sc.bvh, o, d, 0.0f, 1e9f, st, alpha, nullptr);
+    const float pdf_bsdf = r0.w;
+    float3 le = f3(0.0f);
+    float pdf_light;
+    bool contributes = true;
+    if (h.face == kNoHit) {
+      // __miss__light: environment radiance, cosine pdf of the sky NEE strategy
+      le = sky_radiance(sc, d);
+      pdf_light = r2.w / kPi;
+    } else {
+      // __closesthit__light: an emitter record only for emissive, front-facing faces
+      const fredholm::Material& m = sc.materials[sc.material_ids[h.face]];
+      pdf_light = r2.w / kPi;
+      contributes = false;
+      if (is_emissive(m)) {
+        const FaceGeom g = load_face(sc, sc.indices[h.face], sc.face_submesh[h.face]);
+        const float3 nl = bary3(g.n0, g.n1, g.n2, h.u, h.v);
+        const float cos_l = dot(-d, nl);
+        if (cos_l > 0.0f) {
+          const float3 p = bary3(g.v0, g.v1, g.v2, h.u, h.v);
+          const float2 uv = bary2(g.t0, g.t1, g.t2, h.u, h.v);
+          const SceneTex tex{sc.textures, sc.srgb_lut};
+          le = emission_of(m, tex, uv);
+          const float area = 0.5f * length(cross(g.v1 - g.v0, g.v2 - g.v0));
+          const float3 dp = p - o;
+          const float r2d = dot(dp, dp);
+          const float pdf_area = 1.0f / (sc.n_lights * area);
+          pdf_light = r2d / fabsf(cos_l) * pdf_area;
+          contributes = true;
+        }
+      }
+    }
+    if (contributes) {
+      const float mis = pdf_bsdf / (pdf_bsdf + pdf_light);
+      const float3 w = clamp3(f3(r2.x * mis, r2.y * mis, r2.z * mis), 0.0f, 1.0f);
+      const uint32_t path = __float_as_uint(r1.w);
+      float4 L = wb.L[path];
+      L.x += w.x * le.x;
+      L.y += w.y * le.y;
+      L.z += w.z * le.z;
+      wb.L[path] = L;
+    }
+  }
+}
+
+// stand-alone batch query for the parity tests
+__global__ void __launch_bounds__(kBlock) k_trace_batch(SceneView sc, const uint32_t* __restrict__ submesh_offsets,
+                                                        const float* __restrict__ rays, uint32_t n, float tmin,
+                                                        float tmax, uint32_t* __restrict__ out_id,
+                                                        float* __restrict__ out_tuv, unsigned long long* counters)
+{
+  FR_DECLARE_STACK();
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float3 o = f3(rays[6ull * i], rays[6ull * i + 1], rays[6ull * i + 2]);
+  const float3 d = f3(rays[6ull * i + 3], rays[6ull * i + 4], rays[6ull * i + 5]);
+  TraceCounters cnt{0, 0};
+  const HitRecord h = traverse<false, true>(sc.bvh, o, d, tmin, tmax, st, NoAnyHit{}, &cnt);
+  if (h.face != kNoHit) {
+    const uint32_t sm = sc.face_submesh[h.face];
+    out_id[2ull * i] = sm;
+    out_id[2ull * i + 1] = h.face - submesh_offsets[sm];
+    out_tuv[3ull * i] = h.t;
+    out_tuv[3ull * i + 1] = h.u;
+    out_tuv[3ull * i + 2] = h.v;
+  } else {
+    out_id[2ull * i] = out_id[2ull * i + 1] = kNoHit;
+    out_tuv[3ull * i] = out_tuv[3ull * i + 1] = out_tuv[3ull * i + 2] = 0.0f;
+  }
+  if (counters) {
+    atomicAdd(&counters[0], (unsigned long long)cnt.nodes);
+    atomicAdd(&counters[1], (unsigned long long)cnt.tris);
+  }
+}
+
+int g_grid_closest = 0, g_grid_shadow = 0, g_grid_light = 0;
+
+int persistent_grid(const void* kernel, int block)
+{
+  int dev = 0, sms = 0, per_sm = 0;
+  FR_CUDA_CHECK(cudaGetDevice(&dev));
+  FR_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  FR_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, 0));
+  return sms * (per_sm > 0 ? per_sm : 1);
+}
+
+}  // namespace
+
+void launch_trace_closest(cudaStream_t s, const SceneView& sc, const WaveBuffers& wb, uint32_t depth)
+{
+  if (!g_grid_closest) g_grid_closest = persistent_grid(reinterpret_cast<const void*>(k_trace_closest), kBlock);
+  k_trace_closest<<<g_grid_closest, kBlock, 0, s>>>(sc, wb, depth);
+  FR_CUDA_LAUNCH_CHECK();
+}
+
+void launch_trace_shadow(cudaStream_t s, const SceneView& sc, const WaveBuffers& wb, int which)
+{
+  if (!g_grid_shadow) g_grid_shadow = persistent_grid(reinterpret_cast<const void*>(k_trace_shadow), kBlock);
+  k_trace_shadow<<<g_grid_shadow, kBlock, 0, s>>>(sc, wb, which);
+  FR_CUDA_LAUNCH_CHECK();
+}
+
+void launch_trace_light(cudaStream_t s, const SceneView& sc, const WaveBuffers& wb)
+{
+  if (!g_grid_light) g_grid_light = persistent_grid(reinterpret_cast<const void*>(k_trace_light), kBlock);
+  k_trace_light<<<g_grid_light, kBlock, 0, s>>>(sc, wb);
+  FR_CUDA_LAUNCH_CHECK();
+}
+
+void trace_batch_closest(const SceneView& sc, const uint32_t* d_submesh_offsets, const float* rays_host, uint32_t n,
+                         float tmin, float tmax, uint32_t* out_id_host, float* out_tuv_host,
+                         unsigned long long* counters2_host)
+{
+  if (n == 0) return;
+  DevBuf<float> d_rays(6ull * n), d_tuv(3ull * n);
+  DevBuf<uint32_t> d_id(2ull * n);
+  DevBuf<unsigned long long> d_cnt(2);
+  d_cnt.zero();
+  FR_CUDA_CHECK(cudaMemcpy(d_rays.get(), rays_host, sizeof(float) * 6ull * n, cudaMemcpyHostToDevice));
+  k_trace_batch<<<(n + kBlock - 1) / kBlock, kBlock>>>(sc, d_submesh_offsets, d_rays.get(), n, tmin, tmax, d_id.get(),
+                                                       d_tuv.get(), counters2_host ? d_cnt.get() : nullptr);
+  FR_CUDA_LAUNCH_CHECK();
+  FR_CUDA_CHECK(cudaMemcpy(out_id_host, d_id.get(), sizeof(uint32_t) * 2ull * n, cudaMemcpyDeviceToHost));
+  FR_CUDA_CHECK(cudaMemcpy(out_tuv_host, d_tuv.get(), sizeof(float) * 3ull * n, cudaMemcpyDeviceToHost));
+  if (counters2_host)
+    FR_CUDA_CHECK(cudaMemcpy(counters2_host, d_cnt.get(), sizeof(unsigned long long) * 2, cudaMemcpyDeviceToHost));
+}
+
+}  // namespace frd

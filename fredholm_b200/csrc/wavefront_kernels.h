@@ -1,0 +1,42 @@
+// Host-callable launchers of the wavefront stages (shade.cu, trace.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "wavefront.h"
+
+namespace frd
+{
+
+enum FilmMode : int {
+  FILM_MEAN = 0,  // reference behaviour: streaming mean into the layers (pt.cu:480-501)
+  FILM_SUM = 1,   // accumulate sums (multi-GPU sample slices; divide after the reduce)
+};
+
+// shade.cu
+void launch_wave_begin(cudaStream_t s, const WaveBuffers& wb, unsigned long long n_paths);
+void launch_generate(cudaStream_t s, const WaveParams& wp, const WaveBuffers& wb);
+void launch_shade(cudaStream_t s, const WaveParams& wp, const SceneView& sc, const WaveBuffers& wb, uint32_t depth);
+void launch_advance(cudaStream_t s, const WaveBuffers& wb);
+void launch_film(cudaStream_t s, const WaveParams& wp, const WaveBuffers& wb, const fredholm::RenderLayer& layers,
+                 int film_mode);
+void launch_scale_layers(cudaStream_t s, const fredholm::RenderLayer& layers, uint32_t n_pixels, float scale);
+
+// trace.cu
+void launch_trace_closest(cudaStream_t s, const SceneView& sc, const WaveBuffers& wb, uint32_t depth);
+void launch_trace_shadow(cudaStream_t s, const SceneView& sc, const WaveBuffers& wb, int which);
+void launch_trace_light(cudaStream_t s, const SceneView& sc, const WaveBuffers& wb);
+// stand-alone batch query (tests, tools): rays are (o.xyz, d.xyz) per entry;
+// out_id = (instance, primitive) or 0xffffffff, out_tuv = (t, u, v).  All HOST pointers.
+// counters (optional, host): nodes visited, triangles tested
+void trace_batch_closest(const SceneView& sc, const uint32_t* d_submesh_offsets, const float* rays_host, uint32_t n,
+                         float tmin, float tmax, uint32_t* out_id_host, float* out_tuv_host,
+                         unsigned long long* counters2_host);
+
+// unit-test entry points (shade.cu)
+void test_sampler(uint32_t width, uint32_t height, uint32_t seed, uint32_t image_idx, uint32_t n_spp,
+                  const char* kinds, float* out_host, uint32_t n_out);
+void test_bsdf(const float* in_host, uint32_t n, float* out_host);
+void test_sky(const SceneView& sc, const float* dirs_host, uint32_t n, float* out_host);
+void test_primary_rays(const WaveParams& wp, float* out_host);
+
+}  // namespace frd

@@ -1,0 +1,291 @@
+"""Procedural scenes for the tests and the benchmark (no network, no assets: the
+reference ships no scenes either).
+
+Every generator is deterministic (fixed integer hashes, no RNG state) and returns
+SceneArrays -- exactly the flat arrays fredholm::Scene holds -- so the same data can
+be handed to the CUDA core (fr_set_scene_arrays) and to the host oracle
+(orc_set_scene).  `write_obj` serialises a scene as .obj/.mtl text to exercise the
+file loaders on both sides.
+
+  cornell_box()            BASELINE.json config 1: ~32 triangles, Lambert-like + quad light
+  standard_surface_scene() BASELINE.json config 2/3: terrain + spheres, 1 048 576
+                           triangles by default, 8 Standard-Surface materials
+                           (metal / coat / rough glass / sheen / diffuse)
+"""
+import os
+
+import numpy as np
+
+from .types import MATERIAL_DTYPE, SceneArrays, make_material
+
+
+# --------------------------------------------------------------------------------------
+def _quad(p0, p1, p2, p3):
+    """Two triangles (p0,p1,p2), (p0,p2,p3)."""
+    return [(p0, p1, p2), (p0, p2, p3)]
+
+
+def _assemble(tris_by_shape, materials):
+    """tris_by_shape: list of shapes; each shape = list of (tri (3x3), material id).
+    Vertices are de-duplicated on (position, normal, texcoord) in order of first use,
+    like the reference's .obj path (scene.cpp:317-393); normals are face normals and
+    texcoords the loader's defaults for faces without vt (scene.cpp:363-379)."""
+    verts, lookup = [], {}
+    indices, mat_ids, offsets, counts = [], [], [], []
+    for shape in tris_by_shape:
+        offsets.append(len(indices))
+        for tri, mid in shape:
+            p = np.asarray(tri, dtype=np.float32)
+            e1 = p[1] - p[0]
+            e2 = p[2] - p[0]
+            e1 = e1 * (np.float32(1) / np.sqrt(np.dot(e1, e1)))
+            e2 = e2 * (np.float32(1) / np.sqrt(np.dot(e2, e2)))
+            n = np.cross(e1, e2).astype(np.float32)
+            n = n * (np.float32(1) / np.sqrt(np.dot(n, n)))
+            uv = [(0.0, 0.0), (1.0, 0.0), (0.0, 1.0)]
+            ids = []
+            for k in range(3):
+                key = (p[k].tobytes(), n.astype(np.float32).tobytes(), uv[k])
+                if key not in lookup:
+                    lookup[key] = len(verts)
+                    verts.append((p[k], n, uv[k]))
+                ids.append(lookup[key])
+            indices.append(ids)
+            mat_ids.append(mid)
+        counts.append(len(indices) - offsets[-1])
+    return SceneArrays(
+        vertices=np.array([v[0] for v in verts], np.float32),
+        normals=np.array([v[1] for v in verts], np.float32),
+        texcoords=np.array([v[2] for v in verts], np.float32),
+        indices=np.array(indices, np.uint32), material_ids=np.array(mat_ids, np.uint32),
+        materials=np.array(materials, dtype=MATERIAL_DTYPE),
+        submesh_offsets=np.array(offsets, np.uint32), submesh_n_faces=np.array(counts, np.uint32))
+
+
+def _box(cx, cz, sx, sy, sz, angle_deg):
+    """Axis box of size (sx,sy,sz) standing on y=0, rotated about y; bottom face omitted."""
+    a = np.deg2rad(angle_deg)
+    c, s = np.cos(a), np.sin(a)
+
+    def P(x, y, z):
+        return (cx + c * x + s * z, y, cz - s * x + c * z)
+
+    hx, hz = sx / 2, sz / 2
+    b = [P(-hx, 0, -hz), P(hx, 0, -hz), P(hx, 0, hz), P(-hx, 0, hz)]
+    t = [P(-hx, sy, -hz), P(hx, sy, -hz), P(hx, sy, hz), P(-hx, sy, hz)]
+    tris = []
+    tris += _quad(t[0], t[3], t[2], t[1])  # top (normal +y)
+    tris += _quad(b[3], b[2], t[2], t[3])  # +z side
+    tris += _quad(b[2], b[1], t[1], t[2])  # +x side
+    tris += _quad(b[1], b[0], t[0], t[1])  # -z side
+    tris += _quad(b[0], b[3], t[3], t[0])  # -x side
+    return tris
+
+
+def cornell_box():
+    """Cornell box in x in [-1,1], y in [0,2], z in [-1,1], open towards +z.
+    Materials are Lambert-like: Kd set, specular colour 0 (specular lobe off),
+    metalness 0, opaque; one quad light with emission (17, 12, 4)."""
+    white = make_material(base_color=(0.725, 0.71, 0.68), specular_color=(0, 0, 0))
+    red = make_material(base_color=(0.63, 0.065, 0.05), specular_color=(0, 0, 0))
+    green = make_material(base_color=(0.14, 0.45, 0.091), specular_color=(0, 0, 0))
+    light = make_material(base_color=(0.78, 0.78, 0.78), specular_color=(0, 0, 0), emission=1.0,
+                          emission_color=(17, 12, 4))
+    materials = [white, red, green, light]
+    W, R, G, Lm = 0, 1, 2, 3
+    room = []
+    room += [(t, W) for t in _quad((-1, 0, 1), (1, 0, 1), (1, 0, -1), (-1, 0, -1))]    # floor (+y)
+    room += [(t, W) for t in _quad((-1, 2, -1), (1, 2, -1), (1, 2, 1), (-1, 2, 1))]    # ceiling (-y)
+    room += [(t, W) for t in _quad((-1, 0, -1), (1, 0, -1), (1, 2, -1), (-1, 2, -1))]  # back (+z)
+    room += [(t, R) for t in _quad((-1, 0, 1), (-1, 0, -1), (-1, 2, -1), (-1, 2, 1))]  # left (+x)
+    room += [(t, G) for t in _quad((1, 0, -1), (1, 0, 1), (1, 2, 1), (1, 2, -1))]      # right (-x)
+    lamp = [(t, Lm) for t in _quad((-0.25, 1.98, -0.25), (0.25, 1.98, -0.25), (0.25, 1.98, 0.25),
+                                   (-0.25, 1.98, 0.25))]                               # light (-y)
+    short = [(t, W) for t in _box(0.33, 0.35, 0.6, 0.6, 0.6, -18.0)]
+    tall = [(t, W) for t in _box(-0.35, -0.3, 0.6, 1.2, 0.6, 17.0)]
+    return _assemble([room, lamp, short, tall], materials)
+
+
+# The thin-lens model puts the lens 1/tan(fov/2) behind `origin` (camera.cu:24-53): with
+# fov 45 deg the eye sits at z = 1.15 + 2.414 and the box opening just fills the frame.
+CORNELL_CAMERA = dict(origin=(0.0, 1.0, 1.15), fov=np.deg2rad(45.0), F=100.0, focus=10000.0)
+
+
+# --------------------------------------------------------------------------------------
+def _hash_u32(x):
+    """Integer hash (lowbias32) on uint32 arrays."""
+    x = np.asarray(x, dtype=np.uint64) & 0xFFFFFFFF
+    x ^= x >> 16
+    x = (x * 0x7FEB352D) & 0xFFFFFFFF
+    x ^= x >> 15
+    x = (x * 0x846CA68B) & 0xFFFFFFFF
+    x ^= x >> 16
+    return x.astype(np.uint32)
+
+
+def _hash01(x):
+    return (_hash_u32(x).astype(np.float64) / 4294967296.0).astype(np.float32)
+
+
+def standard_surface_materials():
+    """8 materials cycling metal / coated dielectric / rough glass / sheen / diffuse."""
+    return [
+        make_material(base_color=(0.35, 0.37, 0.30), specular_color=(0.04, 0.04, 0.04),
+                      specular_roughness=0.5, diffuse_roughness=0.3),                          # 0 ground
+        make_material(base_color=(0.95, 0.64, 0.54), specular_color=(1, 1, 1), metalness=1.0,
+                      specular_roughness=0.05),                                                # 1 polished copper
+        make_material(base_color=(0.91, 0.92, 0.92), specular_color=(1, 1, 1), metalness=1.0,
+                      specular_roughness=0.5),                                                 # 2 rough aluminium
+        make_material(base_color=(0.7, 0.05, 0.05), specular_color=(1, 1, 1), coat=1.0,
+                      coat_roughness=0.05, specular_roughness=0.3),                            # 3 car paint
+        make_material(base_color=(1, 1, 1), specular_color=(1, 1, 1), transmission=0.9,
+                      transmission_color=(0.9, 1.0, 0.95), specular_roughness=0.15),           # 4 rough glass
+        make_material(base_color=(0.1, 0.15, 0.5), specular_color=(0, 0, 0), sheen=1.0,
+                      sheen_color=(0.8, 0.8, 1.0), sheen_roughness=0.3),                       # 5 sheen cloth
+        make_material(base_color=(0.8, 0.8, 0.2), specular_color=(0, 0, 0)),                   # 6 plain diffuse
+        make_material(base_color=(0.2, 0.6, 0.3), specular_color=(1, 1, 1), specular_roughness=0.1,
+                      coat=0.5, coat_color=(1.0, 0.9, 0.8)),                                   # 7 glossy plastic
+    ]
+
+
+def standard_surface_scene(terrain_res=512, n_spheres=512, sphere_res=(32, 16), seed=0xF2ED401):
+    """Terrain (terrain_res^2 quads) + n_spheres UV spheres of 2*sphere_res[0]*sphere_res[1]
+    triangles.  Defaults: 524 288 + 512 * 1024 = 1 048 576 triangles.  One sub-mesh for the
+    terrain and one per sphere, identity transforms."""
+    R = terrain_res
+    ext = 40.0
+    # ---- terrain: value-noise heightfield on a (R+1)^2 grid ----
+    gx, gz = np.meshgrid(np.arange(R + 1), np.arange(R + 1), indexing="xy")
+    x = (gx.astype(np.float32) / R - 0.5) * ext
+    z = (gz.astype(np.float32) / R - 0.5) * ext
+
+    def value_noise(cells):
+        cx = gx.astype(np.float64) / R * cells
+        cz = gz.astype(np.float64) / R * cells
+        ix, iz = np.floor(cx).astype(np.int64), np.floor(cz).astype(np.int64)
+        fx, fz = cx - ix, cz - iz
+        fx, fz = fx * fx * (3 - 2 * fx), fz * fz * (3 - 2 * fz)
+
+        def lat(a, b):
+            return _hash01((a * 73856093 ^ b * 19349663 ^ (seed + cells)) & 0xFFFFFFFF).astype(np.float64)
+        v = (lat(ix, iz) * (1 - fx) + lat(ix + 1, iz) * fx) * (1 - fz) + \
+            (lat(ix, iz + 1) * (1 - fx) + lat(ix + 1, iz + 1) * fx) * fz
+        return v
+
+    h = (1.6 * value_noise(4) + 0.8 * value_noise(8) + 0.35 * value_noise(16) + 0.12 * value_noise(48))
+    y = (h - h.mean()).astype(np.float32)
+    tv = np.stack([x, y, z], axis=-1).reshape(-1, 3)
+    # normals by central differences
+    dx = np.zeros_like(y)
+    dz = np.zeros_like(y)
+    dx[:, 1:-1] = (y[:, 2:] - y[:, :-2]) / (2 * ext / R)
+    dx[:, 0], dx[:, -1] = (y[:, 1] - y[:, 0]) / (ext / R), (y[:, -1] - y[:, -2]) / (ext / R)
+    dz[1:-1, :] = (y[2:, :] - y[:-2, :]) / (2 * ext / R)
+    dz[0, :], dz[-1, :] = (y[1, :] - y[0, :]) / (ext / R), (y[-1, :] - y[-2, :]) / (ext / R)
+    tn = np.stack([-dx, np.ones_like(dx), -dz], axis=-1).reshape(-1, 3)
+    tn /= np.linalg.norm(tn, axis=1, keepdims=True)
+    tt = np.stack([gx.astype(np.float32) / R * 8, gz.astype(np.float32) / R * 8], axis=-1).reshape(-1, 2)
+    i0 = (gz[:-1, :-1] * (R + 1) + gx[:-1, :-1]).reshape(-1)
+    i1, i2, i3 = i0 + 1, i0 + (R + 1) + 1, i0 + (R + 1)
+    # counter-clockwise seen from +y
+    tf = np.concatenate([np.stack([i0, i3, i2], 1), np.stack([i0, i2, i1], 1)], axis=1).reshape(-1, 3)
+
+    verts, norms, texs, faces, mats = [tv], [tn.astype(np.float32)], [tt], [tf], [np.zeros(len(tf), np.uint32)]
+    offsets, counts = [0], [len(tf)]
+    vbase, fbase = len(tv), len(tf)
+
+    # ---- spheres on a jittered grid, resting on the terrain ----
+    nu, nv = sphere_res
+    uu, vv = np.meshgrid(np.arange(nu + 1), np.arange(nv + 1), indexing="xy")
+    phi = uu.astype(np.float64) / nu * 2 * np.pi
+    theta = vv.astype(np.float64) / nv * np.pi
+    unit = np.stack([np.sin(theta) * np.cos(phi), np.cos(theta), np.sin(theta) * np.sin(phi)], -1).reshape(-1, 3)
+    st = np.stack([uu / nu, vv / nv], -1).reshape(-1, 2).astype(np.float32)
+    a = (vv[:-1, :-1] * (nu + 1) + uu[:-1, :-1]).reshape(-1)
+    b, c, d = a + 1, a + (nu + 1) + 1, a + (nu + 1)
+    sf = np.concatenate([np.stack([a, b, c], 1), np.stack([a, c, d], 1)], axis=1).reshape(-1, 3)
+    side = int(np.ceil(np.sqrt(n_spheres)))
+    ids = np.arange(n_spheres)
+    jx = _hash01(ids * 2 + 1 + seed) - 0.5
+    jz = _hash01(ids * 2 + 2 + seed) - 0.5
+    rad = 0.28 + 0.42 * _hash01(ids + 977 + seed)
+    cxs = ((ids % side + 0.5 + 0.6 * jx) / side - 0.5) * (ext * 0.9)
+    czs = ((ids // side + 0.5 + 0.6 * jz) / side - 0.5) * (ext * 0.9)
+    # terrain height under the centre (nearest grid vertex)
+    ixs = np.clip(np.round((cxs / ext + 0.5) * R).astype(int), 0, R)
+    izs = np.clip(np.round((czs / ext + 0.5) * R).astype(int), 0, R)
+    cys = y[izs, ixs] + rad * (0.9 + 1.5 * _hash01(ids + 4242 + seed))
+    for s in range(n_spheres):
+        centre = np.array([cxs[s], cys[s], czs[s]], dtype=np.float64)
+        verts.append((centre + rad[s] * unit).astype(np.float32))
+        norms.append(unit.astype(np.float32))
+        texs.append(st)
+        faces.append(sf + vbase)
+        mats.append(np.full(len(sf), 1 + (s % 7), np.uint32))
+        offsets.append(fbase)
+        counts.append(len(sf))
+        vbase += len(unit)
+        fbase += len(sf)
+    return SceneArrays(vertices=np.concatenate(verts), normals=np.concatenate(norms),
+                       texcoords=np.concatenate(texs), indices=np.concatenate(faces).astype(np.uint32),
+                       material_ids=np.concatenate(mats),
+                       materials=np.array(standard_surface_materials(), dtype=MATERIAL_DTYPE),
+                       submesh_offsets=np.array(offsets, np.uint32), submesh_n_faces=np.array(counts, np.uint32))
+
+
+STANDARD_CAMERA = dict(origin=(0.0, 6.0, 22.0), fov=np.deg2rad(50.0), F=16.0, focus=20.0)
+# rtcamp8 lighting (rtcamp8.cpp:142-146)
+STANDARD_LIGHTING = dict(sun_le=(20.0, 20.0, 20.0), sun_dir=(-0.1, 1.0, 0.1), sun_angle=1.0,
+                         turbidity=3.0, albedo=0.3)
+
+
+# --------------------------------------------------------------------------------------
+_MTL_KEYS = ("diffuse", "diffuse_roughness", "sheen", "sheen_color", "sheen_roughness", "subsurface",
+             "subsurface_color", "thin_walled")
+
+
+def write_obj(scene: SceneArrays, directory, name="scene", with_attributes=True):
+    """Serialises `scene` as name.obj + name.mtl (one `o` per sub-mesh).  With
+    with_attributes=False only positions are written, so the loaders have to supply
+    face normals and default texcoords.  Returns the .obj path."""
+    os.makedirs(directory, exist_ok=True)
+    obj_path = os.path.join(directory, name + ".obj")
+    with open(os.path.join(directory, name + ".mtl"), "w") as f:
+        for i, m in enumerate(scene.materials):
+            f.write("newmtl m%d\n" % i)
+            f.write("Kd %.9g %.9g %.9g\n" % tuple(m["base_color"]))
+            f.write("Ks %.9g %.9g %.9g\n" % tuple(m["specular_color"]))
+            if any(m["emission_color"] > 0):
+                f.write("Ke %.9g %.9g %.9g\n" % tuple(m["emission_color"]))
+            f.write("Pr %.9g\nPm %.9g\n" % (m["specular_roughness"], m["metalness"]))
+            if m["coat"] > 0:
+                f.write("Pc %.9g\nPcr %.9g\n" % (m["coat"], m["coat_roughness"]))
+            f.write("d %.9g\n" % (1.0 - m["transmission"]))
+            f.write("Tf %.9g %.9g %.9g\n" % tuple(m["transmission_color"]))
+            f.write("diffuse %.9g\ndiffuse_roughness %.9g\n" % (m["diffuse"], m["diffuse_roughness"]))
+            f.write("sheen %.9g\nsheen_color %.9g %.9g %.9g\nsheen_roughness %.9g\n" %
+                    (m["sheen"], *m["sheen_color"], m["sheen_roughness"]))
+            f.write("subsurface %.9g\nsubsurface_color %.9g %.9g %.9g\nthin_walled %.9g\n" %
+                    (m["subsurface"], *m["subsurface_color"], m["thin_walled"]))
+    with open(obj_path, "w") as f:
+        f.write("mtllib %s.mtl\n" % name)
+        f.write("".join("v %.9g %.9g %.9g\n" % tuple(v) for v in scene.vertices))
+        if with_attributes:
+            f.write("".join("vn %.9g %.9g %.9g\n" % tuple(v) for v in scene.normals))
+            f.write("".join("vt %.9g %.9g\n" % tuple(v) for v in scene.texcoords))
+        for s, (off, cnt) in enumerate(zip(scene.submesh_offsets, scene.submesh_n_faces)):
+            f.write("o shape%d\n" % s)
+            cur = -1
+            lines = []
+            for fi in range(int(off), int(off + cnt)):
+                mid = int(scene.material_ids[fi])
+                if mid != cur:
+                    lines.append("usemtl m%d\n" % mid)
+                    cur = mid
+                a, b, c = (int(v) + 1 for v in scene.indices[fi])
+                if with_attributes:
+                    lines.append("f %d/%d/%d %d/%d/%d %d/%d/%d\n" % (a, a, a, b, b, b, c, c, c))
+                else:
+                    lines.append("f %d %d %d\n" % (a, b, c))
+            f.write("".join(lines))
+    return obj_path

@@ -1,0 +1,124 @@
+// fredholm::Renderer -- the rendering core behind the application-facing API.
+//
+// Same call surface as the reference's header-only OptiX renderer
+// (fredholm/include/fredholm/renderer.h:29-846): applications call, in order,
+//   create_module -> create_program_group -> create_pipeline -> set_resolution ->
+//   load_scene -> build_gas -> build_ias -> create_sbt -> render(...) ->
+//   wait_for_completion
+// (app/controller.cpp:60-68,126-134; app/rtcamp8.cpp:79-124).  Here the OptiX
+// pipeline steps are no-ops kept for source compatibility: the kernels are
+// hand-written sm_100a code linked into libfredholm_b200.so, build_gas() builds
+// the GPU LBVH -> CWBVH over all sub-meshes and build_ias() is folded into it
+// (one world-space tree).  The only intentional signature change is the
+// constructor (no OptixDeviceContext): Renderer(int cuda_device).
+//
+// render() is "canonical mode" of the reference: n_samples samples are taken as
+// n_samples launches of one sample each would take them.
+// Errors surface as std::runtime_error with file:line, like the reference's
+// CUDA_CHECK / OPTIX_CHECK.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <filesystem>
+#include <memory>
+
+#include "fredholm/camera.h"
+#include "fredholm/scene.h"
+#include "fredholm/shared.h"
+
+namespace fredholm
+{
+
+enum class FilmMode : int {
+  MEAN = 0,  // streaming mean into the layers (reference behaviour)
+  SUM = 1,   // running sums; divide by the sample count after a multi-GPU reduce
+};
+
+struct RenderStatistics {
+  unsigned long long paths = 0;
+  unsigned long long rays_radiance = 0;
+  unsigned long long rays_shadow = 0;
+  unsigned long long rays_light = 0;
+  unsigned long long kernel_launches = 0;
+  unsigned long long total_rays() const { return rays_radiance + rays_shadow + rays_light; }
+};
+
+struct AccelInfo {
+  uint32_t n_faces = 0;
+  uint32_t n_nodes = 0;
+  uint32_t depth = 0;
+  float build_ms = 0.0f;
+  size_t bytes = 0;
+};
+
+class Renderer
+{
+ public:
+  explicit Renderer(int cuda_device = 0);
+  ~Renderer() noexcept(false);
+  Renderer(const Renderer&) = delete;
+  Renderer& operator=(const Renderer&) = delete;
+
+  // ---- OptiX pipeline steps of the reference: no-ops here ----
+  void create_module(const std::filesystem::path& filepath);
+  void create_program_group();
+  void create_pipeline();
+  void create_sbt();
+
+  // ---- scene ----
+  void load_scene(const std::filesystem::path& filepath, bool clear = true);
+  // extension: adopt an already filled Scene (procedural content)
+  void set_scene(const Scene& scene);
+  const Scene& get_scene() const;
+  void build_gas();
+  void build_ias();
+  void set_time(float time);
+
+  // ---- lights / sky ----
+  void set_directional_light(const float3& le, const float3& dir, float angle);
+  void clear_directional_light();  // extension
+  void set_sky_intensity(float sky_intensity);
+  void load_ibl(const std::filesystem::path& filepath);
+  void set_ibl(const float4* texels, uint32_t width, uint32_t height);  // extension
+  void clear_ibl();
+  void load_arhosek_sky(float turbidity, float albedo);
+  void clear_arhosek_sky();
+
+  // ---- film ----
+  void set_resolution(uint32_t width, uint32_t height);
+  void init_render_states();
+
+  // ---- render ----
+  void render(const Camera& camera, const float3& bg_color, const RenderLayer& render_layer, uint32_t n_samples,
+              uint32_t max_depth);
+  // same, with the camera given as the packed parameter block
+  void render(const CameraParams& camera, const float3& bg_color, const RenderLayer& render_layer,
+              uint32_t n_samples, uint32_t max_depth);
+  void wait_for_completion();
+
+  // ---- extensions for multi-GPU sample slicing and tuning ----
+  void set_sample_offset(uint32_t first_sample);  // next render starts at this sample index
+  uint32_t get_sample_count() const;
+  void set_film_mode(FilmMode mode);
+  void scale_layers(const RenderLayer& render_layer, float scale);
+  void set_max_wave_paths(size_t n_paths);
+  RenderStatistics get_statistics();
+  void reset_statistics();
+  AccelInfo get_accel_info() const;
+  cudaStream_t get_stream() const;
+  int get_device() const;
+
+  struct Impl;
+  Impl* impl() { return m_impl.get(); }
+
+ private:
+  std::unique_ptr<Impl> m_impl;
+};
+
+// Hosek-Wilkie RGB sky coefficients for (turbidity, ground albedo, solar elevation):
+// out = 3 x 9 configuration values followed by 3 mean radiances
+// (reference arhosek.h:145-323).
+void arhosek_rgb_cook(float turbidity, float albedo, float elevation, float out30[30]);
+
+}  // namespace fredholm

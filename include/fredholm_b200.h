@@ -1,0 +1,169 @@
+/* C ABI of libfredholm_b200.so -- the drop-in boundary of the B200 rendering core.
+ *
+ * The reference exposes its hot path as a C++ class API (fredholm::Renderer,
+ * fredholm/include/fredholm/renderer.h), not as an FFI; the C++ mirror of that
+ * API is include/fredholm/renderer.h.  This header flattens the same calls to
+ * plain C (pointers + sizes, no C++ or torch types) so that any host language
+ * can bind them (ctypes / cgo / JNI).  Every entry names the reference interface
+ * it stands for.  All functions return 0 on success and -1 on failure unless
+ * stated otherwise; fr_last_error() then returns the message of the C++
+ * exception (the reference reports errors as std::runtime_error, cwl/util.h:11-56).
+ *
+ * Pointer conventions: `const float*` / `const uint32_t*` arguments are HOST
+ * pointers unless the name ends in `_dev`.  Matrices: `transforms` are
+ * column-major 4x4 (glm::mat4 layout, 16 floats); camera transforms are the
+ * row-major 3x4 camera-to-world block (12 floats) that Renderer::render packs
+ * into CameraParams (renderer.h:678-684).
+ */
+#ifndef FREDHOLM_B200_H
+#define FREDHOLM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct fr_renderer fr_renderer;
+
+/* six AOV buffers of shared.h:201-208 (float4 per pixel, depth: float per pixel);
+ * NULL entries (except beauty) are skipped */
+typedef struct fr_layers {
+  void* beauty;
+  void* position;
+  void* depth;
+  void* normal;
+  void* texcoord;
+  void* albedo;
+} fr_layers;
+
+/* kernels/post-process.h:4-10 */
+typedef struct fr_post_process_params {
+  int use_bloom;
+  float bloom_threshold;
+  float bloom_sigma;
+  float ISO;
+  float chromatic_aberration;
+} fr_post_process_params;
+
+const char* fr_last_error(void);
+int fr_device_count(void);
+/* version string: "fredholm_b200 <semver> sm_100a" */
+const char* fr_version(void);
+
+/* ---- lifetime: Renderer(ctx) / ~Renderer (renderer.h:32-122) ---- */
+fr_renderer* fr_renderer_create(int cuda_device);
+void fr_renderer_destroy(fr_renderer* r);
+
+/* ---- scene: Renderer::load_scene (renderer.h:354-432), Scene arrays (scene.h:107-130) ---- */
+int fr_load_scene(fr_renderer* r, const char* path, int clear);
+/* staged textures are attached by the next fr_set_scene_arrays; returns the texture id */
+int fr_stage_texture(fr_renderer* r, const uint8_t* rgba8, uint32_t width, uint32_t height, int is_color);
+int fr_set_scene_arrays(fr_renderer* r, const float* vertices, const float* normals, const float* texcoords,
+                        uint32_t n_vertices, const uint32_t* indices, const uint32_t* material_ids,
+                        const uint32_t* instance_ids, uint32_t n_faces, const void* materials /* 180 B each */,
+                        uint32_t n_materials, const uint32_t* submesh_offsets, const uint32_t* submesh_n_faces,
+                        const float* transforms, uint32_t n_submeshes);
+/* loader introspection: out6 = n_vertices, n_faces, n_materials, n_textures, n_submeshes, has_camera */
+int fr_get_scene_sizes(fr_renderer* r, uint32_t* out6);
+int fr_get_scene_arrays(fr_renderer* r, float* vertices, float* normals, float* texcoords, uint32_t* indices,
+                        uint32_t* material_ids, uint32_t* instance_ids, void* materials, uint32_t* submesh_offsets,
+                        uint32_t* submesh_n_faces, float* transforms, float* camera_transform16);
+int fr_get_texture_info(fr_renderer* r, uint32_t i, uint32_t* width, uint32_t* height, uint32_t* is_color);
+int fr_get_texture_data(fr_renderer* r, uint32_t i, uint8_t* rgba8);
+/* Renderer::build_gas + build_ias (renderer.h:434-552): GPU LBVH -> CWBVH */
+int fr_build_accel(fr_renderer* r);
+/* out3 = n_faces, n_nodes, depth */
+int fr_get_accel_info(fr_renderer* r, uint32_t* out3, float* build_ms, uint64_t* bytes);
+/* Renderer::set_time (renderer.h:614-640) and direct transform replacement */
+int fr_set_time(fr_renderer* r, float time);
+int fr_set_transforms(fr_renderer* r, const float* transforms, uint32_t n_submeshes);
+
+/* ---- stand-alone Scene (host only, no GPU needed): Scene::load_model (scene.cpp:103-117) ---- */
+typedef struct fr_scene fr_scene;
+fr_scene* fr_scene_create(void);
+void fr_scene_destroy(fr_scene* s);
+int fr_scene_load(fr_scene* s, const char* path, int clear);
+int fr_scene_get_sizes(fr_scene* s, uint32_t* out6);
+int fr_scene_get_arrays(fr_scene* s, float* vertices, float* normals, float* texcoords, uint32_t* indices,
+                        uint32_t* material_ids, uint32_t* instance_ids, void* materials, uint32_t* submesh_offsets,
+                        uint32_t* submesh_n_faces, float* transforms, float* camera_transform16);
+int fr_scene_get_texture_info(fr_scene* s, uint32_t i, uint32_t* width, uint32_t* height, uint32_t* is_color);
+int fr_scene_get_texture_data(fr_scene* s, uint32_t i, uint8_t* rgba8);
+/* Scene::update_animation (scene.cpp:862-898) */
+int fr_scene_update_animation(fr_scene* s, float time);
+/* hands the scene to a renderer (Renderer::load_scene's upload part) */
+int fr_set_scene(fr_renderer* r, const fr_scene* s);
+
+/* ---- lights / sky (renderer.h:554-612) ---- */
+int fr_set_directional_light(fr_renderer* r, const float* le3, const float* dir3, float angle_deg);
+int fr_clear_directional_light(fr_renderer* r);
+int fr_set_sky_intensity(fr_renderer* r, float sky_intensity);
+int fr_load_arhosek_sky(fr_renderer* r, float turbidity, float albedo);
+int fr_clear_arhosek_sky(fr_renderer* r);
+int fr_set_ibl(fr_renderer* r, const float* rgba32f, uint32_t width, uint32_t height);
+int fr_load_ibl(fr_renderer* r, const char* path);
+int fr_clear_ibl(fr_renderer* r);
+
+/* ---- film (renderer.h:642-655) ---- */
+int fr_set_resolution(fr_renderer* r, uint32_t width, uint32_t height);
+int fr_init_render_states(fr_renderer* r);
+int fr_set_sample_offset(fr_renderer* r, uint32_t first_sample);
+uint32_t fr_get_sample_count(fr_renderer* r);
+/* 0 = streaming mean (reference), 1 = sums (multi-GPU slices) */
+int fr_set_film_mode(fr_renderer* r, int mode);
+int fr_set_max_wave_paths(fr_renderer* r, uint64_t n_paths);
+
+/* ---- render: Renderer::render / wait_for_completion (renderer.h:657-736) ----
+ * layers hold DEVICE pointers owned by the caller; asynchronous on the renderer's stream */
+int fr_render(fr_renderer* r, const float* camera_transform12, float fov, float F, float focus, const float* bg_color3,
+              const fr_layers* layers_dev, uint32_t n_samples, uint32_t max_depth);
+int fr_wait(fr_renderer* r);
+/* one whole frame through HOST buffers: clears internal device layers, renders n_samples,
+ * copies the non-NULL layers back (cwl::CUDABuffer::copy_from_device_to_host, buffer.h:64-69)
+ * and waits.  This is the call the end-to-end benchmark times. */
+int fr_render_frame_host(fr_renderer* r, const float* camera_transform12, float fov, float F, float focus,
+                         const float* bg_color3, const fr_layers* layers_host, uint32_t n_samples, uint32_t max_depth);
+int fr_scale_layers(fr_renderer* r, const fr_layers* layers_dev, float scale);
+/* out5 = paths, radiance rays, shadow rays, light rays, kernel launches */
+int fr_get_statistics(fr_renderer* r, uint64_t* out5);
+int fr_reset_statistics(fr_renderer* r);
+/* CUDA stream of the renderer as an integer handle (cudaStream_t) */
+uint64_t fr_get_stream(fr_renderer* r);
+
+/* ---- post-process: kernels/post-process.cu:5-47 (device pointers, float4 per pixel) ---- */
+int fr_post_process(const void* beauty_in_dev, void* high_luminance_dev, void* temp_dev, int width, int height,
+                    const fr_post_process_params* params, void* beauty_out_dev);
+int fr_tone_mapping(const void* beauty_in_dev, int width, int height, float ISO, float chromatic_aberration,
+                    void* beauty_out_dev);
+
+/* ---- raw device memory helpers (cwl::CUDABuffer, buffer.h:18-85) ---- */
+void* fr_device_alloc(size_t bytes);
+int fr_device_free(void* p);
+int fr_device_memset(void* p, int value, size_t bytes);
+int fr_copy_to_device(void* dst_dev, const void* src_host, size_t bytes);
+int fr_copy_to_host(void* dst_host, const void* src_dev, size_t bytes);
+int fr_device_synchronize(void);
+
+/* ---- stage-level entry points used by the parity tests ---- */
+/* closest hit for n rays (6 floats each: origin, direction): out_id = (instance, primitive)
+ * or 0xffffffff, out_tuv = (t, u, v); counters2 (optional) = nodes visited, triangles tested */
+int fr_trace_closest(fr_renderer* r, const float* rays, uint32_t n, float tmin, float tmax, uint32_t* out_id,
+                     float* out_tuv, uint64_t* counters2);
+int fr_primary_rays(fr_renderer* r, const float* camera_transform12, float fov, float F, float focus, uint32_t n_spp,
+                    float* out_rays);
+int fr_sampler_sequence(uint32_t width, uint32_t height, uint32_t seed, uint32_t image_idx, uint32_t n_spp,
+                        const char* kinds, float* out);
+/* in: n x 40 floats (ShadingParams[30], wo[3], entering, wi[3], u, v[2]); out: n x 11 floats */
+int fr_bsdf_eval_sample(const float* in, uint32_t n, float* out);
+int fr_sky_radiance(fr_renderer* r, const float* dirs, uint32_t n, float* out);
+int fr_arhosek_cook(float turbidity, float albedo, float elevation, float* out30);
+/* fredholm::Camera mirror (camera.h:51-135) */
+int fr_camera_transform(const float* origin3, float* out12);
+int fr_camera_walk(const float* origin3, float d_phi, float d_theta, int movement, float dt, float* out12);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FREDHOLM_B200_H */
