@@ -90,6 +90,12 @@ SIGNATURES = {
     "fr_scale_layers": (C.c_int, [_vp, C.POINTER(_Layers), C.c_float]),
     "fr_get_statistics": (C.c_int, [_vp, _u64p]),
     "fr_reset_statistics": (C.c_int, [_vp]),
+    "fr_set_stage_timing": (C.c_int, [_vp, C.c_int]),
+    "fr_get_stage_times": (C.c_int, [_vp, C.POINTER(C.c_double), _u64p]),
+    "fr_event_create": (_vp, []),
+    "fr_event_destroy": (C.c_int, [_vp]),
+    "fr_event_record": (C.c_int, [_vp, _vp]),
+    "fr_event_elapsed_ms": (C.c_int, [_vp, _vp, _fp]),
     "fr_get_stream": (C.c_uint64, [_vp]),
     "fr_post_process": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.POINTER(_PostProcessParams), _vp]),
     "fr_tone_mapping": (C.c_int, [_vp, C.c_int, C.c_int, C.c_float, C.c_float, _vp]),
@@ -99,6 +105,8 @@ SIGNATURES = {
     "fr_copy_to_device": (C.c_int, [_vp, _vp, C.c_size_t]),
     "fr_copy_to_host": (C.c_int, [_vp, _vp, C.c_size_t]),
     "fr_device_synchronize": (C.c_int, []),
+    "fr_host_alloc_pinned": (_vp, [C.c_size_t]),
+    "fr_host_free_pinned": (C.c_int, [_vp]),
     "fr_trace_closest": (C.c_int, [_vp, _fp, C.c_uint32, C.c_float, C.c_float, _up, _fp, _u64p]),
     "fr_primary_rays": (C.c_int, [_vp, _fp, C.c_float, C.c_float, C.c_float, C.c_uint32, _fp]),
     "fr_sampler_sequence": (C.c_int, [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_char_p, _fp]),
@@ -167,6 +175,26 @@ class Camera:
 
 
 LAYER_NAMES = ("beauty", "position", "depth", "normal", "texcoord", "albedo")
+STAGE_NAMES = ("generate", "trace_closest", "shade", "trace_shadow", "trace_light", "advance", "film")
+
+
+def pinned_array(shape, dtype=np.float32):
+    """numpy array backed by page-locked host memory (never freed: benchmark helper)."""
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    p = lib().fr_host_alloc_pinned(n)
+    if not p:
+        raise FredholmError(lib().fr_last_error().decode())
+    buf = (C.c_char * n).from_address(p)
+    return np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+
+def event_elapsed_ms(ev0, ev1, destroy=True):
+    ms = C.c_float()
+    _check(lib().fr_event_elapsed_ms(ev0, ev1, C.byref(ms)))
+    if destroy:
+        lib().fr_event_destroy(ev0)
+        lib().fr_event_destroy(ev1)
+    return ms.value
 
 
 class DeviceLayers:
@@ -436,6 +464,23 @@ class Renderer:
 
     def stream(self):
         return int(lib().fr_get_stream(self._h))
+
+    def set_stage_timing(self, on=True):
+        _check(lib().fr_set_stage_timing(self._h, 1 if on else 0))
+
+    def stage_times(self):
+        """{stage: (total ms, launches)} since the last call (device time, CUDA events)."""
+        ms = (C.c_double * 7)()
+        n = (C.c_uint64 * 7)()
+        _check(lib().fr_get_stage_times(self._h, ms, n))
+        return {name: (ms[i], int(n[i])) for i, name in enumerate(STAGE_NAMES)}
+
+    def record_event(self):
+        ev = lib().fr_event_create()
+        if not ev:
+            raise FredholmError(lib().fr_last_error().decode())
+        _check(lib().fr_event_record(self._h, ev))
+        return ev
 
     # ---- stage-level queries (parity tests) ----
     def trace_closest(self, rays, tmin=0.0, tmax=1e9, counters=False):

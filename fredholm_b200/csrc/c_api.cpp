@@ -421,6 +421,39 @@ int fr_reset_statistics(fr_renderer* r)
 {
   return guarded([&] { r->renderer.reset_statistics(); });
 }
+int fr_set_stage_timing(fr_renderer* r, int on)
+{
+  return guarded([&] { r->renderer.set_stage_timing(on != 0); });
+}
+int fr_get_stage_times(fr_renderer* r, double* ms7, uint64_t* launches7)
+{
+  return guarded([&] {
+    unsigned long long l[Renderer::kStageCount];
+    r->renderer.get_stage_times(ms7, l);
+    for (int i = 0; i < Renderer::kStageCount; ++i) launches7[i] = l[i];
+  });
+}
+void* fr_event_create(void)
+{
+  cudaEvent_t e = nullptr;
+  if (guarded([&] { FR_CUDA_CHECK(cudaEventCreate(&e)); }) != 0) return nullptr;
+  return e;
+}
+int fr_event_destroy(void* ev)
+{
+  return guarded([&] { FR_CUDA_CHECK(cudaEventDestroy(static_cast<cudaEvent_t>(ev))); });
+}
+int fr_event_record(fr_renderer* r, void* ev)
+{
+  return guarded([&] { FR_CUDA_CHECK(cudaEventRecord(static_cast<cudaEvent_t>(ev), r->renderer.get_stream())); });
+}
+int fr_event_elapsed_ms(void* ev_start, void* ev_stop, float* ms)
+{
+  return guarded([&] {
+    FR_CUDA_CHECK(cudaEventSynchronize(static_cast<cudaEvent_t>(ev_stop)));
+    FR_CUDA_CHECK(cudaEventElapsedTime(ms, static_cast<cudaEvent_t>(ev_start), static_cast<cudaEvent_t>(ev_stop)));
+  });
+}
 uint64_t fr_get_stream(fr_renderer* r) { return reinterpret_cast<uint64_t>(r->renderer.get_stream()); }
 
 int fr_post_process(const void* beauty_in_dev, void* high_luminance_dev, void* temp_dev, int width, int height,
@@ -471,6 +504,16 @@ int fr_copy_to_device(void* dst_dev, const void* src_host, size_t bytes)
 int fr_copy_to_host(void* dst_host, const void* src_dev, size_t bytes)
 {
   return guarded([&] { FR_CUDA_CHECK(cudaMemcpy(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost)); });
+}
+void* fr_host_alloc_pinned(size_t bytes)
+{
+  void* p = nullptr;
+  if (guarded([&] { FR_CUDA_CHECK(cudaMallocHost(&p, bytes)); }) != 0) return nullptr;
+  return p;
+}
+int fr_host_free_pinned(void* p)
+{
+  return guarded([&] { FR_CUDA_CHECK(cudaFreeHost(p)); });
 }
 int fr_device_synchronize(void)
 {

@@ -5,6 +5,58 @@
 namespace frd
 {
 
+Integrator::~Integrator()
+{
+  for (auto& t : m_timed) {
+    cudaEventDestroy(t.e0);
+    cudaEventDestroy(t.e1);
+  }
+  for (auto e : m_event_pool) cudaEventDestroy(e);
+}
+
+cudaEvent_t Integrator::get_event()
+{
+  if (!m_event_pool.empty()) {
+    cudaEvent_t e = m_event_pool.back();
+    m_event_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e;
+  FR_CUDA_CHECK(cudaEventCreate(&e));
+  return e;
+}
+
+template <typename F>
+void Integrator::stage(int id, F&& launch)
+{
+  if (!m_time_stages) {
+    launch();
+  } else {
+    TimedLaunch t{id, get_event(), get_event()};
+    FR_CUDA_CHECK(cudaEventRecord(t.e0, m_stream));
+    launch();
+    FR_CUDA_CHECK(cudaEventRecord(t.e1, m_stream));
+    m_timed.push_back(t);
+  }
+  m_launches++;
+}
+
+StageTimes Integrator::stage_times()
+{
+  StageTimes out;
+  FR_CUDA_CHECK(cudaStreamSynchronize(m_stream));
+  for (auto& t : m_timed) {
+    float ms = 0.0f;
+    FR_CUDA_CHECK(cudaEventElapsedTime(&ms, t.e0, t.e1));
+    out.ms[t.stage] += ms;
+    out.launches[t.stage]++;
+    m_event_pool.push_back(t.e0);
+    m_event_pool.push_back(t.e1);
+  }
+  m_timed.clear();
+  return out;
+}
+
 void Integrator::ensure_capacity(size_t n_slots)
 {
   if (m_ctl.size() == 0) {
@@ -64,29 +116,18 @@ void Integrator::render(const SceneView& scene, const fredholm::CameraParams& ca
     wp.seed = seed;
     wp.camera = camera;
 
-    launch_wave_begin(m_stream, wb, (unsigned long long)wp.n_samples * width * height);
-    launch_generate(m_stream, wp, wb);
-    m_launches += 2;
+    stage(STAGE_ADVANCE, [&] { launch_wave_begin(m_stream, wb, (unsigned long long)wp.n_samples * width * height); });
+    stage(STAGE_GENERATE, [&] { launch_generate(m_stream, wp, wb); });
     for (uint32_t depth = 0; depth < max_depth; ++depth) {
-      launch_trace_closest(m_stream, scene, wb, depth);
-      launch_shade(m_stream, wp, scene, wb, depth);
-      m_launches += 2;
-      if (scene.has_dir_light) {
-        launch_trace_shadow(m_stream, scene, wb, 0);
-        m_launches++;
-      }
-      launch_trace_shadow(m_stream, scene, wb, 1);
-      m_launches++;
-      if (scene.n_lights > 0) {
-        launch_trace_shadow(m_stream, scene, wb, 2);
-        m_launches++;
-      }
-      launch_trace_light(m_stream, scene, wb);
-      launch_advance(m_stream, wb);
-      m_launches += 2;
+      stage(STAGE_TRACE_CLOSEST, [&] { launch_trace_closest(m_stream, scene, wb, depth); });
+      stage(STAGE_SHADE, [&] { launch_shade(m_stream, wp, scene, wb, depth); });
+      if (scene.has_dir_light) stage(STAGE_TRACE_SHADOW, [&] { launch_trace_shadow(m_stream, scene, wb, 0); });
+      stage(STAGE_TRACE_SHADOW, [&] { launch_trace_shadow(m_stream, scene, wb, 1); });
+      if (scene.n_lights > 0) stage(STAGE_TRACE_SHADOW, [&] { launch_trace_shadow(m_stream, scene, wb, 2); });
+      stage(STAGE_TRACE_LIGHT, [&] { launch_trace_light(m_stream, scene, wb); });
+      stage(STAGE_ADVANCE, [&] { launch_advance(m_stream, wb); });
     }
-    launch_film(m_stream, wp, wb, layers, film_mode);
-    m_launches++;
+    stage(STAGE_FILM, [&] { launch_film(m_stream, wp, wb, layers, film_mode); });
   }
 }
 

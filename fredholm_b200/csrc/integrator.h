@@ -3,6 +3,7 @@
 // (replaces the single optixLaunch of Renderer::render, renderer.h:730-733).
 #pragma once
 #include <cstdint>
+#include <vector>
 
 #include "cuda_util.h"
 #include "wavefront.h"
@@ -17,6 +18,22 @@ struct RenderStats {
   unsigned long long rays_shadow = 0;   // visibility rays traced
   unsigned long long rays_light = 0;    // MIS rays traced
   unsigned long long launches = 0;      // kernels launched by the integrator
+};
+
+enum Stage : int {
+  STAGE_GENERATE = 0,
+  STAGE_TRACE_CLOSEST,
+  STAGE_SHADE,
+  STAGE_TRACE_SHADOW,
+  STAGE_TRACE_LIGHT,
+  STAGE_ADVANCE,
+  STAGE_FILM,
+  STAGE_COUNT
+};
+
+struct StageTimes {
+  double ms[STAGE_COUNT] = {};
+  unsigned long long launches[STAGE_COUNT] = {};
 };
 
 class Integrator
@@ -42,6 +59,11 @@ class Integrator
 
   size_t state_bytes() const { return m_state_bytes; }
 
+  // per-stage device time (CUDA events around every launch, on the launching stream)
+  void set_stage_timing(bool on) { m_time_stages = on; }
+  StageTimes stage_times();  // synchronises, returns and clears the accumulated times
+  ~Integrator();
+
  private:
   void ensure_capacity(size_t n_slots);
 
@@ -50,6 +72,17 @@ class Integrator
   size_t m_capacity = 0;
   size_t m_state_bytes = 0;
   unsigned long long m_launches = 0;
+
+  struct TimedLaunch {
+    int stage;
+    cudaEvent_t e0, e1;
+  };
+  bool m_time_stages = false;
+  std::vector<TimedLaunch> m_timed;
+  std::vector<cudaEvent_t> m_event_pool;
+  cudaEvent_t get_event();
+  template <typename F>
+  void stage(int id, F&& launch);
 
   DevBuf<float4> m_ray_o, m_ray_d, m_hit, m_thr, m_L, m_aov0, m_aov1, m_aov2;
   DevBuf<uint32_t> m_queue[2];

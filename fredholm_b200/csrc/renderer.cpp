@@ -405,6 +405,17 @@ void Renderer::scale_layers(const RenderLayer& render_layer, float scale)
 }
 void Renderer::set_max_wave_paths(size_t n_paths) { m_impl->integrator->set_max_wave_paths(n_paths); }
 
+void Renderer::set_stage_timing(bool on) { m_impl->integrator->set_stage_timing(on); }
+void Renderer::get_stage_times(double ms[kStageCount], unsigned long long launches[kStageCount])
+{
+  static_assert(kStageCount == frd::STAGE_COUNT, "stage list out of sync");
+  const frd::StageTimes t = m_impl->integrator->stage_times();
+  for (int i = 0; i < kStageCount; ++i) {
+    ms[i] = t.ms[i];
+    launches[i] = t.launches[i];
+  }
+}
+
 RenderStatistics Renderer::get_statistics()
 {
   const frd::RenderStats s = m_impl->integrator->stats();

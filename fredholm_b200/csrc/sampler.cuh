@@ -91,7 +91,13 @@ FR_HD float kensler_randfloat(uint32_t i, uint32_t p)
   i ^= 0xdf6e307fu;
   i ^= i >> 17;
   i *= 1u | p >> 18;
+  // the product must be rounded on its own: callers add to it, and a fused
+  // multiply-add would differ from the host reference in the last bit
+#ifdef __CUDA_ARCH__
+  return __fmul_rn((float)i, 1.0f / 4294967808.0f);
+#else
   return i * (1.0f / 4294967808.0f);
+#endif
 }
 
 // one CMJ point of the 4x4 pattern (cmj.cu:60-69)

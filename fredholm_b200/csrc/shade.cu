@@ -109,7 +109,9 @@ FR_D void load_surface_params(const fredholm::Material& m, const SceneTex& tex, 
     p.metalness = clampf(mr.z, 0.0f, 1.0f);
   }
   p.coat = clampf(m.coat_texture_id >= 0 ? tex.fetch(m.coat_texture_id, uv).x : m.coat, 0.0f, 1.0f);
-  p.coat_color = m.coat_color;
+  // quirk: the reference never copies Material::coat_color into its shading
+  // parameters (pt.cu:238-255), so the coat is always colourless on the device
+  p.coat_color = f3(1.0f);
   p.coat_roughness =
       clampf(m.coat_roughness_texture_id >= 0 ? tex.fetch(m.coat_roughness_texture_id, uv).y : m.coat_roughness,
              0.0f, 1.0f);

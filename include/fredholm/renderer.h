@@ -103,6 +103,11 @@ class Renderer
   void set_film_mode(FilmMode mode);
   void scale_layers(const RenderLayer& render_layer, float scale);
   void set_max_wave_paths(size_t n_paths);
+  // per-stage device time, measured with CUDA events on the renderer's stream;
+  // stages: generate, trace_closest, shade, trace_shadow, trace_light, advance, film
+  static constexpr int kStageCount = 7;
+  void set_stage_timing(bool on);
+  void get_stage_times(double ms[kStageCount], unsigned long long launches[kStageCount]);
   RenderStatistics get_statistics();
   void reset_statistics();
   AccelInfo get_accel_info() const;

@@ -129,6 +129,16 @@ int fr_scale_layers(fr_renderer* r, const fr_layers* layers_dev, float scale);
 /* out5 = paths, radiance rays, shadow rays, light rays, kernel launches */
 int fr_get_statistics(fr_renderer* r, uint64_t* out5);
 int fr_reset_statistics(fr_renderer* r);
+/* per-stage device time from CUDA events on the renderer's stream; 7 stages:
+ * generate, trace_closest, shade, trace_shadow, trace_light, advance, film.
+ * fr_get_stage_times synchronises, returns the accumulated ms / launch counts and clears them */
+int fr_set_stage_timing(fr_renderer* r, int on);
+int fr_get_stage_times(fr_renderer* r, double* ms7, uint64_t* launches7);
+/* CUDA events on the renderer's stream (timing on the launching stream) */
+void* fr_event_create(void);
+int fr_event_destroy(void* ev);
+int fr_event_record(fr_renderer* r, void* ev);
+int fr_event_elapsed_ms(void* ev_start, void* ev_stop, float* ms); /* synchronises on ev_stop */
 /* CUDA stream of the renderer as an integer handle (cudaStream_t) */
 uint64_t fr_get_stream(fr_renderer* r);
 
@@ -145,6 +155,9 @@ int fr_device_memset(void* p, int value, size_t bytes);
 int fr_copy_to_device(void* dst_dev, const void* src_host, size_t bytes);
 int fr_copy_to_host(void* dst_host, const void* src_dev, size_t bytes);
 int fr_device_synchronize(void);
+/* page-locked host memory for the read-back path */
+void* fr_host_alloc_pinned(size_t bytes);
+int fr_host_free_pinned(void* p);
 
 /* ---- stage-level entry points used by the parity tests ---- */
 /* closest hit for n rays (6 floats each: origin, direction): out_id = (instance, primitive)
