@@ -17,6 +17,9 @@
 // that use the same roughness, and evaluates value and pdf in one pass.
 // Local shading frame: +y is the normal.
 #pragma once
+#include <cstdint>
+
+#include "lobes.h"
 #include "vecmath.cuh"
 
 namespace frd
@@ -44,17 +47,6 @@ struct SurfaceParams {
   float subsurface;
   float3 subsurface_color;
   float thin_walled;
-};
-
-enum Lobe : int {
-  LOBE_COAT = 0,
-  LOBE_METAL,
-  LOBE_SPECULAR,
-  LOBE_TRANSMISSION,
-  LOBE_SHEEN,
-  LOBE_DIFFUSE_T,
-  LOBE_DIFFUSE_R,
-  LOBE_COUNT
 };
 
 // ---- small lobe helpers ------------------------------------------------------
@@ -200,13 +192,17 @@ FR_D float3 guard(const float3& v) { return bad3(v) ? f3(0.0f) : v; }
 FR_D float guard(float v) { return (isinf(v) || isnan(v)) ? 0.0f : v; }
 
 // -----------------------------------------------------------------------------
+template <uint32_t MASK>
 struct Closure {
+  static constexpr bool kCoat = MASK & M_COAT, kMetal = MASK & M_METAL, kSpec = MASK & M_SPECULAR,
+                        kTrans = MASK & M_TRANSMISSION, kSheen = MASK & M_SHEEN, kDiffT = MASK & M_DIFFUSE_T;
   float3 wo;
   // layer scalars after the "seen from inside" masking (bsdf.cu:56-62)
   float coat, metalness, specular, transmission, sheen, subsurface, thin_walled, diffuse;
   float3 base_color, specular_color, transmission_color, sheen_color, subsurface_color;
   float3 coat_absorption;
   bool coat_on, spec_on, sheen_on;  // luminance gates (bsdf.cu:132,144,159)
+  bool metal_on, trans_on, difft_on;
   float spec_albedo, sheen_albedo;
   float a_coat, a_spec;  // GGX alpha
   float ni, nt, eta;
@@ -232,12 +228,12 @@ struct Closure {
     const float f0t = (nt - ni) / (nt + ni);
     const float F0 = f0t * f0t;
     float coat_albedo = 0.0f;
-    if (p.coat * coat_lum > 0.0f) coat_albedo = entering ? albedo_ggx(wo.y, p.coat_roughness, F0) : 0.0f;
+    if (kCoat && p.coat * coat_lum > 0.0f) coat_albedo = entering ? albedo_ggx(wo.y, p.coat_roughness, F0) : 0.0f;
     spec_albedo = 0.0f;
-    if (p.specular * spec_lum > 0.0f)
+    if (kSpec && p.specular * spec_lum > 0.0f)
       spec_albedo = eta >= 1.0f ? albedo_ggx(wo.y, p.specular_roughness, F0) : 0.0f;
     sheen_albedo = 0.0f;
-    if (p.sheen * sheen_lum) sheen_albedo = entering ? albedo_sheen(wo.y, p.sheen_roughness) : 0.0f;
+    if (kSheen && p.sheen * sheen_lum) sheen_albedo = entering ? albedo_sheen(wo.y, p.sheen_roughness) : 0.0f;
 
     coat = entering ? p.coat : 0.0f;
     metalness = entering ? p.metalness : 0.0f;
@@ -252,9 +248,12 @@ struct Closure {
     transmission_color = p.transmission_color;
     sheen_color = p.sheen_color;
     subsurface_color = p.subsurface_color;
-    coat_on = coat * coat_lum > 0.0f;
-    spec_on = specular * spec_lum > 0.0f;
-    sheen_on = sheen * sheen_lum > 0.0f;
+    coat_on = kCoat && coat * coat_lum > 0.0f;
+    spec_on = kSpec && specular * spec_lum > 0.0f;
+    sheen_on = kSheen && sheen * sheen_lum > 0.0f;
+    metal_on = kMetal && metalness > 0.0f;
+    trans_on = kTrans && transmission > 0.0f;
+    difft_on = kDiffT && subsurface * thin_walled > 0.0f;
 
     // layer weights (bsdf.cu:67-93)
     float w[LOBE_COUNT];
@@ -300,7 +299,7 @@ struct Closure {
     const float sigma2 = p.diffuse_roughness * p.diffuse_roughness;
     on_A = 1.0f - (sigma2 / (2.0f * (sigma2 + 0.33f)));
     on_B = 0.45f * sigma2 / (sigma2 + 0.09f);
-    sheen_fit.init(p.sheen_roughness);
+    if (kSheen) sheen_fit.init(p.sheen_roughness);
   }
 
   // ---- per-lobe value / pdf ---------------------------------------------------
@@ -354,7 +353,7 @@ struct Closure {
   FR_D void eval(const float3& wi, float3& f_out, float& pdf_out) const
   {
     const float cos_pdf = abs_cos(wi) / kPi;
-    const bool need_refl = coat_on || spec_on || metalness > 0.0f;
+    const bool need_refl = coat_on || spec_on || metal_on;
     float3 h = f3(0.0f);
     if (need_refl || sheen_on) h = normalize(wo + wi);
 
@@ -366,10 +365,10 @@ struct Closure {
       v_coat = guard(f3(fresnel_dielectric(fabsf(dot(wo, h)), eta) * dg));
       p_coat = guard(pdf);
     }
-    if (spec_on || metalness > 0.0f) {
+    if (spec_on || metal_on) {
       float dg, pdf;
       ggx_reflect_terms(a_spec, wi, h, dg, pdf);
-      if (metalness > 0.0f) {
+      if (metal_on) {
         v_metal = guard(fresnel_conductor(fabsf(dot(wo, h)), metal_n, metal_k) * dg);
         p_metal = guard(pdf);
       }
@@ -380,7 +379,7 @@ struct Closure {
     }
     float3 v_trans = f3(0.0f);
     float p_trans = 0.0f;
-    if (transmission > 0.0f) {
+    if (trans_on) {
       const float3 ht = transmission_half(wi);
       v_trans = guard(transmission_value(wi, ht));
       p_trans = guard(transmission_pdf(wi, ht));
@@ -393,9 +392,9 @@ struct Closure {
     }
     float3 v_dt = f3(0.0f), v_dr = f3(0.0f);
     float p_dt = 0.0f, p_dr = 0.0f;
-    if (subsurface * thin_walled > 0.0f || diffuse > 0.0f) {
+    if (difft_on || diffuse > 0.0f) {
       const float3 on = guard(base_color * oren_nayar_scale(on_A, on_B, wo, wi));
-      if (subsurface * thin_walled > 0.0f) {
+      if (difft_on) {
         v_dt = on;
         p_dt = guard(cos_pdf);
       }
@@ -449,10 +448,19 @@ struct Closure {
     float prob;
     const int lobe = pick_lobe(u, prob);
     float3 wi;
-    switch (lobe) {
+    // lobes outside MASK have zero probability; their cases compile away
+    int lobe_c = lobe;
+    if (!kCoat && lobe_c == LOBE_COAT) lobe_c = LOBE_DIFFUSE_R;
+    if (!kMetal && lobe_c == LOBE_METAL) lobe_c = LOBE_DIFFUSE_R;
+    if (!kSpec && lobe_c == LOBE_SPECULAR) lobe_c = LOBE_DIFFUSE_R;
+    if (!kTrans && lobe_c == LOBE_TRANSMISSION) lobe_c = LOBE_DIFFUSE_R;
+    if (!kSheen && lobe_c == LOBE_SHEEN) lobe_c = LOBE_DIFFUSE_R;
+    if (!kDiffT && lobe_c == LOBE_DIFFUSE_T) lobe_c = LOBE_DIFFUSE_R;
+    switch (lobe_c) {
       case LOBE_COAT:
       case LOBE_METAL:
       case LOBE_SPECULAR: {
+        if (!(kCoat || kMetal || kSpec)) break;
         const float a = lobe == LOBE_COAT ? a_coat : a_spec;
         const float3 h = sample_vndf(wo, a, v);
         wi = mirror(wo, h);
@@ -472,6 +480,7 @@ struct Closure {
         pdf = p;
       } break;
       case LOBE_TRANSMISSION: {
+        if (!kTrans) break;
         const float3 h = sample_vndf(wo, a_spec, v);
         const float3 th = -ni / nt * (wo - dot(wo, h) * h);
         const float th2 = dot(th, th);
@@ -495,6 +504,7 @@ struct Closure {
              (1.0f - specular * specular_color * spec_albedo) * transmission * transmission_color;
       } break;
       case LOBE_SHEEN: {
+        if (!kSheen) break;
         const float3 h = cosine_hemisphere_local(v);
         wi = mirror(wo, h);
         f = sheen_value(wi) * (coat_absorption * (1.0f - metalness) *
@@ -503,6 +513,7 @@ struct Closure {
         pdf = abs_cos(wi) / kPi;
       } break;
       case LOBE_DIFFUSE_T: {
+        if (!kDiffT) break;
         wi = -cosine_hemisphere_local(v);
         f = base_color * oren_nayar_scale(on_A, on_B, wo, wi) *
             (coat_absorption * (1.0f - metalness) *

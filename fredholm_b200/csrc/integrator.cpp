@@ -77,14 +77,16 @@ void Integrator::ensure_capacity(size_t n_slots)
   m_queue[0].alloc(n_slots);
   m_queue[1].alloc(n_slots);
   for (auto& s : m_shadow) s.alloc(n_slots);
+  for (auto& q : m_class_queue) q.alloc(n_slots);
   m_light.alloc(n_slots);
   m_capacity = n_slots;
-  m_state_bytes = n_slots * (8 * sizeof(float4) + 2 * sizeof(uint32_t) + 3 * sizeof(ShadowRay) + sizeof(LightRay));
+  m_state_bytes = n_slots * (8 * sizeof(float4) + (2 + CLS_COUNT) * sizeof(uint32_t) + 3 * sizeof(ShadowRay) +
+                             sizeof(LightRay));
 }
 
 void Integrator::render(const SceneView& scene, const fredholm::CameraParams& camera, uint32_t width,
                         uint32_t height, const fredholm::RenderLayer& layers, uint32_t sample_base,
-                        uint32_t n_samples, uint32_t max_depth, uint32_t seed, int film_mode)
+                        uint32_t n_samples, uint32_t max_depth, uint32_t seed, int film_mode, uint32_t class_mask)
 {
   if (width == 0 || height == 0 || n_samples == 0) return;
   const FilmGeom film = make_film_geom(width, height);
@@ -104,6 +106,7 @@ void Integrator::render(const SceneView& scene, const fredholm::CameraParams& ca
   wb.queue[0] = m_queue[0].get();
   wb.queue[1] = m_queue[1].get();
   for (int k = 0; k < 3; ++k) wb.shadow[k] = m_shadow[k].get();
+  for (int c = 0; c < CLS_COUNT; ++c) wb.class_queue[c] = m_class_queue[c].get();
   wb.light = m_light.get();
   wb.ctl = m_ctl.get();
 
@@ -120,7 +123,9 @@ void Integrator::render(const SceneView& scene, const fredholm::CameraParams& ca
     stage(STAGE_GENERATE, [&] { launch_generate(m_stream, wp, wb); });
     for (uint32_t depth = 0; depth < max_depth; ++depth) {
       stage(STAGE_TRACE_CLOSEST, [&] { launch_trace_closest(m_stream, scene, wb, depth); });
-      stage(STAGE_SHADE, [&] { launch_shade(m_stream, wp, scene, wb, depth); });
+      if (depth == 0) stage(STAGE_SHADE, [&] { launch_miss(m_stream, scene, wb); });
+      for (int c = 0; c < CLS_MISS; ++c)
+        if (class_mask & (1u << c)) stage(STAGE_SHADE, [&] { launch_shade(m_stream, wp, scene, wb, depth, c); });
       if (scene.has_dir_light) stage(STAGE_TRACE_SHADOW, [&] { launch_trace_shadow(m_stream, scene, wb, 0); });
       stage(STAGE_TRACE_SHADOW, [&] { launch_trace_shadow(m_stream, scene, wb, 1); });
       if (scene.n_lights > 0) stage(STAGE_TRACE_SHADOW, [&] { launch_trace_shadow(m_stream, scene, wb, 2); });

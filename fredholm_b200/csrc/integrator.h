@@ -46,10 +46,11 @@ class Integrator
   size_t max_wave_paths() const { return m_max_wave_paths; }
 
   // Renders samples [sample_base, sample_base + n_samples) of every pixel into
-  // `layers` (device pointers).  Asynchronous on the stream.
+  // `layers` (device pointers).  Asynchronous on the stream.  class_mask: bit c set if
+  // the scene has materials of ShadeClass c (only those shade kernels are launched).
   void render(const SceneView& scene, const fredholm::CameraParams& camera, uint32_t width, uint32_t height,
               const fredholm::RenderLayer& layers, uint32_t sample_base, uint32_t n_samples, uint32_t max_depth,
-              uint32_t seed, int film_mode);
+              uint32_t seed, int film_mode, uint32_t class_mask);
 
   void scale_layers(const fredholm::RenderLayer& layers, uint32_t n_pixels, float scale);
 
@@ -86,6 +87,7 @@ class Integrator
 
   DevBuf<float4> m_ray_o, m_ray_d, m_hit, m_thr, m_L, m_aov0, m_aov1, m_aov2;
   DevBuf<uint32_t> m_queue[2];
+  DevBuf<uint32_t> m_class_queue[CLS_COUNT];
   DevBuf<ShadowRay> m_shadow[3];
   DevBuf<LightRay> m_light;
   DevBuf<WaveControl> m_ctl;

@@ -13,6 +13,7 @@
 #include <stdexcept>
 #include <vector>
 
+#include "lobes.h"
 #include "renderer_impl.h"
 
 namespace fredholm
@@ -57,6 +58,44 @@ Matrix3x4 rows_of(const mat4& m)
 {
   return make_mat3x4(make_float4(m[0][0], m[1][0], m[2][0], m[3][0]), make_float4(m[0][1], m[1][1], m[2][1], m[3][1]),
                      make_float4(m[0][2], m[1][2], m[2][2], m[3][2]));
+}
+
+float lum(const float3& c) { return 0.2126729f * c.x + 0.7151522f * c.y + 0.0721750f * c.z; }
+
+// Smallest shade-kernel variant whose lobe set covers everything this material can
+// ever evaluate.  A lobe may only be dropped when its run-time gate in the BSDF is
+// provably false (or its layer factor exactly zero) for the material's constants.
+frd::ShadeClass classify_material(const Material& m)
+{
+  using namespace frd;
+  const bool textured = m.base_color_texture_id >= 0 || m.specular_color_texture_id >= 0 ||
+                        m.specular_roughness_texture_id >= 0 || m.metalness_texture_id >= 0 ||
+                        m.metallic_roughness_texture_id >= 0 || m.coat_texture_id >= 0 ||
+                        m.coat_roughness_texture_id >= 0 || m.emission_texture_id >= 0 ||
+                        m.heightmap_texture_id >= 0 || m.normalmap_texture_id >= 0 || m.alpha_texture_id >= 0;
+  if (textured) return CLS_GENERIC_TEX;
+  uint32_t need = M_DIFFUSE_R;
+  if (m.coat > 0.0f) need |= M_COAT;  // coat colour is always white on the device
+  if (m.metalness > 0.0f) need |= M_METAL;
+  const bool full_metal = m.metalness == 1.0f;  // everything under the metal layer is scaled by exactly 0
+  if (!full_metal) {
+    if (m.specular * lum(m.specular_color) > 0.0f) need |= M_SPECULAR;
+    if (m.transmission > 0.0f) need |= M_TRANSMISSION;
+    if (m.sheen * lum(m.sheen_color) != 0.0f) need |= M_SHEEN;
+    if (m.subsurface * m.thin_walled > 0.0f) need |= M_DIFFUSE_T;
+  }
+  const struct {
+    ShadeClass cls;
+    uint32_t mask;
+  } variants[] = {{CLS_DIFFUSE, M_DIFFUSE_R},
+                  {CLS_PLASTIC, M_SPECULAR | M_DIFFUSE_R},
+                  {CLS_METAL, M_METAL | M_DIFFUSE_R},
+                  {CLS_COATED, M_COAT | M_SPECULAR | M_DIFFUSE_R},
+                  {CLS_GLASS, M_SPECULAR | M_TRANSMISSION | M_DIFFUSE_R},
+                  {CLS_SHEEN, M_SHEEN | M_DIFFUSE_R}};
+  for (const auto& v : variants)
+    if ((need & ~v.mask) == 0) return v.cls;
+  return CLS_GENERIC;
 }
 
 float3 normalized(const float3& v)
@@ -143,6 +182,15 @@ void Renderer::Impl::upload_scene()
   }
   d_face_submesh.upload(face_submesh, stream);
   d_face_flags.upload(face_flags, stream);
+  // material class per face (shade-stage queue selection)
+  std::vector<uint8_t> material_class(s.m_materials.size()), face_class(s.m_indices.size());
+  class_mask = 0;
+  for (size_t i = 0; i < s.m_materials.size(); ++i) material_class[i] = (uint8_t)classify_material(s.m_materials[i]);
+  for (size_t f = 0; f < s.m_indices.size(); ++f) {
+    face_class[f] = material_class[s.m_material_ids[f]];
+    class_mask |= 1u << face_class[f];
+  }
+  d_face_class.upload(face_class, stream);
 
   // textures
   d_texture_data.clear();
@@ -213,6 +261,7 @@ frd::SceneView Renderer::Impl::view(const float3& bg_color) const
   v.indices = d_indices.get();
   v.material_ids = d_material_ids.get();
   v.face_submesh = d_face_submesh.get();
+  v.face_class = d_face_class.get();
   v.materials = d_materials.get();
   v.textures = d_textures.get();
   v.srgb_lut = d_srgb_lut.get();
@@ -385,7 +434,8 @@ void Renderer::render(const CameraParams& camera, const float3& bg_color, const 
   const frd::SceneView view = m_impl->view(bg_color);
   m_impl->integrator->render(view, camera, m_impl->width, m_impl->height, render_layer, m_impl->sample_count,
                              n_samples, max_depth, /*seed=*/1u,
-                             m_impl->film_mode == FilmMode::MEAN ? frd::FILM_MEAN : frd::FILM_SUM);
+                             m_impl->film_mode == FilmMode::MEAN ? frd::FILM_MEAN : frd::FILM_SUM,
+                             m_impl->class_mask);
   m_impl->sample_count += n_samples;
 }
 

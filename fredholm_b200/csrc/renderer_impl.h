@@ -26,6 +26,8 @@ struct Renderer::Impl {
   frd::DevBuf<float2> d_texcoords;
   frd::DevBuf<uint3> d_indices;
   frd::DevBuf<uint32_t> d_material_ids, d_face_submesh, d_face_flags, d_submesh_offsets;
+  frd::DevBuf<uint8_t> d_face_class;
+  uint32_t class_mask = 0;  // ShadeClass values present in the scene
   frd::DevBuf<Material> d_materials;
   std::vector<frd::DevBuf<uchar4>> d_texture_data;
   frd::DevBuf<frd::TexView> d_textures;

@@ -169,9 +169,19 @@ struct PathSampler {
 #ifdef FR_HAVE_TABLES
   FR_D float next1d()
   {
-    const uint32_t* m = g_sobol_matrices + 32u * sobol_dim;
+    // the 32 columns of this dimension are one 128-byte line: eight independent 16-byte
+    // loads (usually warp-uniform) and 32 masked XORs, no data-dependent load chain
+    const uint4* m = reinterpret_cast<const uint4*>(g_sobol_matrices + 32u * sobol_dim);
     uint32_t v = 0;
-    for (uint32_t idx = sobol_index; idx; idx &= idx - 1) v ^= __ldg(m + (__ffs(idx) - 1));
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const uint4 w = __ldg(m + q);
+      const uint32_t b = sobol_index >> (4 * q);
+      v ^= w.x & (0u - (b & 1u));
+      v ^= w.y & (0u - ((b >> 1) & 1u));
+      v ^= w.z & (0u - ((b >> 2) & 1u));
+      v ^= w.w & (0u - ((b >> 3) & 1u));
+    }
     const uint32_t r = owen_scramble(v, seed_mix(seed_hash, sobol_dim));
     sobol_dim++;
     return r * (1.0f / 4294967296.0f);

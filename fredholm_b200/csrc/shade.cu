@@ -9,6 +9,7 @@
 // launch ("canonical mode"): every sample starts with a
 // fresh payload, so `firsthit` is simply "bounce 0".
 #include <cstring>
+#include <stdexcept>
 
 #include "tables.cuh"
 //
@@ -81,40 +82,38 @@ __global__ void __launch_bounds__(kBlock) k_generate(WaveParams wp, WaveBuffers 
 }
 
 // ---- shade ----------------------------------------------------------------------------
-struct ShadeOut {
-  bool has_shadow[3];
-  ShadowRay shadow[3];
-  bool has_light;
-  LightRay light;
-  bool continues;
-};
-
+template <bool TEX>
 FR_D void load_surface_params(const fredholm::Material& m, const SceneTex& tex, const float2& uv,
                               SurfaceParams& p)
 {
   // texture-or-constant resolution of the material inputs (pt.cu:181-280)
   p.diffuse = m.diffuse;
   p.diffuse_roughness = m.diffuse_roughness;
-  p.base_color = m.base_color_texture_id >= 0 ? f3(tex.fetch(m.base_color_texture_id, uv)) : m.base_color;
+  p.base_color = m.base_color;
   p.specular = m.specular;
-  p.specular_color =
-      m.specular_color_texture_id >= 0 ? f3(tex.fetch(m.specular_color_texture_id, uv)) : m.specular_color;
-  p.specular_roughness = clampf(
-      m.specular_roughness_texture_id >= 0 ? tex.fetch(m.specular_roughness_texture_id, uv).x : m.specular_roughness,
-      0.01f, 1.0f);
-  p.metalness = m.metalness_texture_id >= 0 ? tex.fetch(m.metalness_texture_id, uv).x : m.metalness;
-  if (m.metallic_roughness_texture_id >= 0) {
+  p.specular_color = m.specular_color;
+  float spec_rough = m.specular_roughness;
+  p.metalness = m.metalness;
+  float coat = m.coat, coat_rough = m.coat_roughness;
+  if (TEX) {
+    if (m.base_color_texture_id >= 0) p.base_color = f3(tex.fetch(m.base_color_texture_id, uv));
+    if (m.specular_color_texture_id >= 0) p.specular_color = f3(tex.fetch(m.specular_color_texture_id, uv));
+    if (m.specular_roughness_texture_id >= 0) spec_rough = tex.fetch(m.specular_roughness_texture_id, uv).x;
+    if (m.metalness_texture_id >= 0) p.metalness = tex.fetch(m.metalness_texture_id, uv).x;
+    if (m.coat_texture_id >= 0) coat = tex.fetch(m.coat_texture_id, uv).x;
+    if (m.coat_roughness_texture_id >= 0) coat_rough = tex.fetch(m.coat_roughness_texture_id, uv).y;
+  }
+  p.specular_roughness = clampf(spec_rough, 0.01f, 1.0f);
+  if (TEX && m.metallic_roughness_texture_id >= 0) {
     const float4 mr = tex.fetch(m.metallic_roughness_texture_id, uv);
     p.specular_roughness = clampf(mr.y, 0.01f, 1.0f);
     p.metalness = clampf(mr.z, 0.0f, 1.0f);
   }
-  p.coat = clampf(m.coat_texture_id >= 0 ? tex.fetch(m.coat_texture_id, uv).x : m.coat, 0.0f, 1.0f);
+  p.coat = clampf(coat, 0.0f, 1.0f);
   // quirk: the reference never copies Material::coat_color into its shading
   // parameters (pt.cu:238-255), so the coat is always colourless on the device
   p.coat_color = f3(1.0f);
-  p.coat_roughness =
-      clampf(m.coat_roughness_texture_id >= 0 ? tex.fetch(m.coat_roughness_texture_id, uv).y : m.coat_roughness,
-             0.0f, 1.0f);
+  p.coat_roughness = clampf(coat_rough, 0.0f, 1.0f);
   p.transmission = m.transmission;
   p.transmission_color = m.transmission_color;
   p.sheen = m.sheen;
@@ -129,292 +128,245 @@ FR_D void load_surface_params(const fredholm::Material& m, const SceneTex& tex, 
 FR_D float3 regularize(const float3& w) { return clamp3(w, 0.0f, 1.0f); }
 FR_D bool nonzero3(const float3& v) { return v.x != 0.0f || v.y != 0.0f || v.z != 0.0f; }
 
-FR_D void set_shadow(ShadowRay& r, const float3& o, const float3& d, float tmax, uint32_t path, const float3& c)
-{
-  r.ox = o.x;
-  r.oy = o.y;
-  r.oz = o.z;
-  r.tmax = tmax;
-  r.dx = d.x;
-  r.dy = d.y;
-  r.dz = d.z;
-  r.path = path;
-  r.cr = c.x;
-  r.cg = c.y;
-  r.cb = c.z;
-  r.pad_ = 0;
-}
-
 constexpr float kShadowEps = 0.001f;  // SHADOW_RAY_EPS, pt.cu:11
 constexpr float kRayMax = 1e9f;
 
-// One path at one bounce.  Returns what has to be enqueued.
-FR_D void shade_path(const WaveParams& wp, const SceneView& sc, const WaveBuffers& wb, uint32_t slot,
-                     uint32_t depth, ShadeOut& out)
+FR_D void add_radiance(const WaveBuffers& wb, uint32_t slot, const float3& v)
 {
-  out.has_shadow[0] = out.has_shadow[1] = out.has_shadow[2] = false;
-  out.has_light = false;
-  out.continues = false;
+  float4 L = wb.L[slot];
+  L.x += v.x;
+  L.y += v.y;
+  L.z += v.z;
+  wb.L[slot] = L;
+}
 
-  const float4 ro = wb.ray_o[slot], rd = wb.ray_d[slot];
-  const float4 hit = wb.hit[slot];
-  const float4 thr4 = wb.thr[slot];
-  const float3 ray_o = f3(ro), ray_d = f3(rd);
-  float3 throughput = f3(thr4);
-  const uint32_t face = __float_as_uint(hit.w);
-
-  if (face == kNoHit) {
-    // __miss__radiance: sky is only added for camera rays; later bounces receive it
-    // through next-event estimation and the MIS ray
-    if (depth == 0) {
-      const float3 le = sky_radiance(sc, ray_d);
-      float4 L = wb.L[slot];
-      L.x += throughput.x * le.x;
-      L.y += throughput.y * le.y;
-      L.z += throughput.z * le.z;
-      wb.L[slot] = L;
-    }
-    return;
-  }
-
-  uint32_t px, py;
-  slot_to_pixel(wp.film, slot % wp.film.slots_per_sample, px, py);
-  PathSampler smp = restore_sampler(wp, slot, px, py, thr4.w);
-
-  // ---- surface (fill_surface_info, pt.cu:141-179) ----
-  const uint3 idx = sc.indices[face];
-  const uint32_t xform = sc.face_submesh[face];
-  const FaceGeom g = load_face(sc, idx, xform);
-  const float bu = hit.y, bv = hit.z;
-  const float3 x = bary3(g.v0, g.v1, g.v2, bu, bv);
-  float3 n_g = normalize(cross(g.v1 - g.v0, g.v2 - g.v0));
-  float3 n_s = normalize(bary3(g.n0, g.n1, g.n2, bu, bv));
-  const float2 uv = bary2(g.t0, g.t1, g.t2, bu, bv);
-  const bool entering = dot(-ray_d, n_g) > 0.0f;
-  if (!entering) {
-    n_s = -n_s;
-    n_g = -n_g;
-  }
-  Frame fr;
-  fr.n = n_s;
-  onb(n_s, fr.t, fr.b);
-
-  const fredholm::Material& mat = sc.materials[sc.material_ids[face]];
-  const SceneTex tex{sc.textures, sc.srgb_lut};
-  SurfaceParams sp;
-  load_surface_params(mat, tex, uv, sp);
-
-  // bump / normal mapping (pt.cu:709-742)
-  if (mat.heightmap_texture_id >= 0) {
-    const TexView& hm = sc.textures[mat.heightmap_texture_id];
-    const float du = 1.0f / hm.width, dv = 1.0f / hm.height;
-    const float v = tex.fetch(mat.heightmap_texture_id, uv).x;
-    const float dfdu = tex.fetch(mat.heightmap_texture_id, make_float2(uv.x + du, uv.y)).x - v;
-    const float dfdv = tex.fetch(mat.heightmap_texture_id, make_float2(uv.x, uv.y + dv)).x - v;
-    const float3 t0 = fr.t, b0 = fr.b;
-    fr.t = normalize(t0 + dfdu * n_s);
-    fr.b = normalize(b0 + dfdv * n_s);
-    fr.n = normalize(cross(fr.t, fr.b));
-  }
-  if (mat.normalmap_texture_id >= 0) {
-    float3 value = f3(tex.fetch(mat.normalmap_texture_id, uv));
-    value = 2.0f * value - 1.0f;
-    // the reference maps through the UNBUMPED frame here (pt.cu:739-740)
-    // (tangent-space map: x -> tangent, y -> bitangent, z -> normal)
-    float3 t0, b0;
-    onb(n_s, t0, b0);
-    fr.n = normalize(value.x * t0 + value.y * b0 + value.z * n_s);
-    onb(fr.n, fr.t, fr.b);
-  }
-
-  if (depth == 0) {
-    // first-hit AOVs and directly visible emitters (pt.cu:745-760)
-    wb.aov0[slot] = make_float4(x.x, x.y, x.z, hit.x);
-    wb.aov1[slot] = make_float4(fr.n.x, fr.n.y, fr.n.z, uv.x);
-    wb.aov2[slot] = make_float4(sp.base_color.x, sp.base_color.y, sp.base_color.z, uv.y);
-    if (is_emissive(mat)) {
-      const float3 le = emission_of(mat, tex, uv);
-      float4 L = wb.L[slot];
-      L.x += throughput.x * le.x;
-      L.y += throughput.y * le.y;
-      L.z += throughput.z * le.z;
-      wb.L[slot] = L;
-      return;
-    }
-  }
-
-  const float3 wo = fr.to_local(-ray_d);
-  Closure bsdf;
-  bsdf.init(wo, sp, entering);
-
-  const float3 shadow_o = offset_origin(x, n_g);
-
-  // ---- next-event estimation (pt.cu:766-890) ----
-  if (sc.has_dir_light) {
-    const float2 u = smp.next2d();
-    const float2 pd = concentric_disk(u);
-    const float3 p = kRayMax * sc.dir_light.dir + sc.dir_disk_radius * (sc.dir_t * pd.x + sc.dir_b * pd.y);
-    const float3 dir = normalize(p - shadow_o);
-    const float3 wi = fr.to_local(dir);
-    float3 f;
-    float pdf_bsdf;
-    bsdf.eval(wi, f, pdf_bsdf);
-    const float mis = 1.0f / (1.0f + pdf_bsdf);
-    const float3 weight = regularize(throughput * mis * f * abs_cos(wi) / 1.0f);
-    const float3 c = weight * sc.dir_light.le;
-    if (nonzero3(c)) {
-      out.has_shadow[0] = true;
-      set_shadow(out.shadow[0], shadow_o, dir, kRayMax - kShadowEps, slot, c);
-    }
-  }
-  {
-    // sky: cosine-hemisphere sample, always drawn (pt.cu:796-857)
-    const float2 u = smp.next2d();
-    const float3 wi = cosine_hemisphere(u);
-    const float3 dir = fr.to_world(wi);
-    float3 f;
-    float pdf_bsdf;
-    bsdf.eval(wi, f, pdf_bsdf);
-    const float pdf = abs_cos(wi) / kPi;
-    const float mis = pdf / (pdf + pdf_bsdf);
-    const float3 weight = regularize(throughput * mis * f * abs_cos(wi) / pdf);
-    const float3 c = weight * sky_radiance(sc, dir);
-    if (nonzero3(c)) {
-      out.has_shadow[1] = true;
-      set_shadow(out.shadow[1], shadow_o, dir, kRayMax - kShadowEps, slot, c);
-    }
-  }
-  if (sc.n_lights > 0) {
-    // uniformly chosen emissive triangle, uniform point on it (pt.cu:282-322, 859-889)
-    const float u1 = smp.next1d();
-    const float2 u2 = smp.next2d();
-    const uint32_t li = min((uint32_t)(u1 * sc.n_lights), sc.n_lights - 1u);
-    const fredholm::AreaLight light = sc.lights[li];
-    const float su = sqrtf(u2.x);
-    const float b0 = 1.0f - su, b1 = u2.y * su;
-    const FaceGeom lg = load_face(sc, light.indices, light.instance_idx);
-    const float3 p = bary3(lg.v0, lg.v1, lg.v2, b0, b1);
-    const float3 n = bary3(lg.n0, lg.n1, lg.n2, b0, b1);
-    const float2 luv = bary2(lg.t0, lg.t1, lg.t2, b0, b1);
-    const float area = 0.5f * length(cross(lg.v1 - lg.v0, lg.v2 - lg.v0));
-    const float pdf_area = 1.0f / (sc.n_lights * area);
-    const float3 to_l = p - shadow_o;
-    const float3 dir = normalize(to_l);
-    const float r = length(to_l);
-    const float cos_l = dot(-dir, n);
-    if (cos_l > 0.0f) {
-      const float3 le = emission_of(sc.materials[light.material_id], tex, luv);
-      const float3 wi = fr.to_local(dir);
-      float3 f;
-      float pdf_bsdf;
-      bsdf.eval(wi, f, pdf_bsdf);
-      const float pdf = r * r / fabsf(cos_l) * pdf_area;
-      const float mis = pdf / (pdf + pdf_bsdf);
-      const float3 weight = regularize(throughput * mis * f * abs_cos(wi) / pdf);
-      const float3 c = weight * le;
-      if (nonzero3(c)) {
-        out.has_shadow[2] = true;
-        set_shadow(out.shadow[2], shadow_o, dir, r - kShadowEps, slot, c);
-      }
-    }
-  }
-
-  // ---- MIS ray: BSDF sample traced towards emitters / sky (pt.cu:892-925) ----
-  {
-    const float u1 = smp.next1d();
-    const float2 u2 = smp.next2d();
-    float3 f;
-    float pdf;
-    const float3 wi = bsdf.sample(u1, u2, f, pdf);
-    const float3 dir = fr.to_world(wi);
-    const bool transmitted = dot(dir, n_g) < 0.0f;
-    const float3 o = offset_origin(x, transmitted ? -n_g : n_g);
-    const float3 w = throughput * f * abs_cos(wi) / pdf;
-    if (nonzero3(w)) {
-      out.has_light = true;
-      LightRay& r = out.light;
-      r.ox = o.x;
-      r.oy = o.y;
-      r.oz = o.z;
-      r.pdf_bsdf = pdf;
-      r.dx = dir.x;
-      r.dy = dir.y;
-      r.dz = dir.z;
-      r.path = slot;
-      r.wr = w.x;
-      r.wg = w.y;
-      r.wb = w.z;
-      r.cos_wi = abs_cos(wi);
-    }
-  }
-
-  // ---- continuation: an independent second BSDF sample (pt.cu:927-943) ----
-  {
-    const float u1 = smp.next1d();
-    const float2 u2 = smp.next2d();
-    float3 f;
-    float pdf;
-    const float3 wi = bsdf.sample(u1, u2, f, pdf);
-    const float3 dir = fr.to_world(wi);
-    throughput *= f * abs_cos(wi) / pdf;
-    const bool transmitted = dot(dir, n_g) < 0.0f;
-    const float3 o = offset_origin(x, transmitted ? -n_g : n_g);
-
-    // raygen loop tail + head of the next iteration (pt.cu:455-471)
-    if (bad3(throughput)) return;
-    if (depth + 1 >= wp.max_depth) return;
-    const float p = clampf(luminance(throughput), 0.0f, 1.0f);
-    const float u = smp.next1d();
-    if (u >= p) return;
-    throughput = throughput / p;
-    wb.ray_o[slot] = make_float4(o.x, o.y, o.z, 0.f);
-    wb.ray_d[slot] = make_float4(dir.x, dir.y, dir.z, 0.f);
-    wb.thr[slot] = make_float4(throughput.x, throughput.y, throughput.z, pack_draws(smp));
-    out.continues = true;
+// camera rays that left the scene: __miss__radiance with firsthit (pt.cu:504-523)
+__global__ void __launch_bounds__(kBlock) k_miss(SceneView sc, WaveBuffers wb)
+{
+  WaveControl* ctl = wb.ctl;
+  const uint32_t n = ctl->n_class[CLS_MISS];
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t slot = wb.class_queue[CLS_MISS][i];
+    const float3 d = f3(wb.ray_d[slot]);
+    const float3 thr = f3(wb.thr[slot]);
+    add_radiance(wb, slot, thr * sky_radiance(sc, d));
   }
 }
 
-__global__ void __launch_bounds__(kBlock) k_shade(WaveParams wp, SceneView sc, WaveBuffers wb, uint32_t depth)
+// One material class at one bounce.  MASK = lobes the class can have, TEX = whether its
+// materials read textures.  Every warp pulls 32 paths of the class queue; the next-event
+// strategies and the two BSDF samples run as (non-unrolled) loops so that the BSDF code
+// exists once per kernel, and queue appends happen with the whole warp converged.
+template <uint32_t MASK, bool TEX>
+__global__ void __launch_bounds__(kBlock) k_shade(WaveParams wp, SceneView sc, WaveBuffers wb, uint32_t depth, int cls)
 {
   WaveControl* ctl = wb.ctl;
-  const uint32_t n = ctl->n[Q_CUR];
-  const uint32_t* q_in = wb.queue[depth & 1u];
+  const uint32_t n = ctl->n_class[cls];
+  const uint32_t* q_in = wb.class_queue[cls];
   uint32_t* q_out = wb.queue[(depth & 1u) ^ 1u];
+  const SceneTex tex{sc.textures, sc.srgb_lut};
   uint32_t item;
-  while (fetch_batch(&ctl->cursor[1], n, item)) {
-    ShadeOut out;
-    out.has_shadow[0] = out.has_shadow[1] = out.has_shadow[2] = false;
-    out.has_light = false;
-    out.continues = false;
+  while (fetch_batch(&ctl->cursor_class[cls], n, item)) {
+    bool active = item < n;
     uint32_t slot = 0;
-    if (item < n) {
+    float3 ray_d = f3(0.f), throughput = f3(0.f), x = f3(0.f), n_g = f3(0.f), shadow_o = f3(0.f);
+    Frame fr;
+    fr.t = fr.n = fr.b = f3(0.f);
+    PathSampler smp;
+    smp.pixel = smp.n_spp = smp.sobol_index = smp.seed_hash = smp.cmj_draws = smp.sobol_dim = 0;
+    Closure<MASK> bsdf;
+
+    if (active) {
       slot = q_in[item];
-      shade_path(wp, sc, wb, slot, depth, out);
+      const float4 rd = wb.ray_d[slot];
+      const float4 hit = wb.hit[slot];
+      const float4 thr4 = wb.thr[slot];
+      ray_d = f3(rd);
+      throughput = f3(thr4);
+      const uint32_t face = __float_as_uint(hit.w);
+      uint32_t px, py;
+      slot_to_pixel(wp.film, slot % wp.film.slots_per_sample, px, py);
+      smp = restore_sampler(wp, slot, px, py, thr4.w);
+
+      // ---- surface (fill_surface_info, pt.cu:141-179) ----
+      const uint3 idx = sc.indices[face];
+      const FaceGeom g = load_face(sc, idx, sc.face_submesh[face]);
+      const float bu = hit.y, bv = hit.z;
+      x = bary3(g.v0, g.v1, g.v2, bu, bv);
+      n_g = normalize(cross(g.v1 - g.v0, g.v2 - g.v0));
+      float3 n_s = normalize(bary3(g.n0, g.n1, g.n2, bu, bv));
+      const float2 uv = bary2(g.t0, g.t1, g.t2, bu, bv);
+      const bool entering = dot(-ray_d, n_g) > 0.0f;
+      if (!entering) {
+        n_s = -n_s;
+        n_g = -n_g;
+      }
+      fr.n = n_s;
+      onb(n_s, fr.t, fr.b);
+
+      const fredholm::Material& mat = sc.materials[sc.material_ids[face]];
+      SurfaceParams sp;
+      load_surface_params<TEX>(mat, tex, uv, sp);
+
+      if (TEX) {
+        // bump / normal mapping (pt.cu:709-742)
+        if (mat.heightmap_texture_id >= 0) {
+          const TexView& hm = sc.textures[mat.heightmap_texture_id];
+          const float du = 1.0f / hm.width, dv = 1.0f / hm.height;
+          const float v = tex.fetch(mat.heightmap_texture_id, uv).x;
+          const float dfdu = tex.fetch(mat.heightmap_texture_id, make_float2(uv.x + du, uv.y)).x - v;
+          const float dfdv = tex.fetch(mat.heightmap_texture_id, make_float2(uv.x, uv.y + dv)).x - v;
+          const float3 t0 = fr.t, b0 = fr.b;
+          fr.t = normalize(t0 + dfdu * n_s);
+          fr.b = normalize(b0 + dfdv * n_s);
+          fr.n = normalize(cross(fr.t, fr.b));
+        }
+        if (mat.normalmap_texture_id >= 0) {
+          float3 value = f3(tex.fetch(mat.normalmap_texture_id, uv));
+          value = 2.0f * value - 1.0f;
+          // the reference maps through the UNBUMPED frame here (pt.cu:739-740)
+          // (tangent-space map: x -> tangent, y -> bitangent, z -> normal)
+          float3 t0, b0;
+          onb(n_s, t0, b0);
+          fr.n = normalize(value.x * t0 + value.y * b0 + value.z * n_s);
+          onb(fr.n, fr.t, fr.b);
+        }
+      }
+
+      if (depth == 0) {
+        // first-hit AOVs and directly visible emitters (pt.cu:745-760)
+        wb.aov0[slot] = make_float4(x.x, x.y, x.z, hit.x);
+        wb.aov1[slot] = make_float4(fr.n.x, fr.n.y, fr.n.z, uv.x);
+        wb.aov2[slot] = make_float4(sp.base_color.x, sp.base_color.y, sp.base_color.z, uv.y);
+        if (is_emissive(mat)) {
+          const float3 le = TEX ? emission_of(mat, tex, uv) : mat.emission_color;
+          add_radiance(wb, slot, throughput * le);
+          active = false;
+        }
+      }
+      if (active) {
+        bsdf.init(fr.to_local(-ray_d), sp, entering);
+        shadow_o = offset_origin(x, n_g);
+      }
     }
-#pragma unroll
+
+    // ---- next-event estimation (pt.cu:766-890): 0 = sun disk, 1 = sky, 2 = area light ----
+#pragma unroll 1
     for (int k = 0; k < 3; ++k) {
-      const uint32_t pos = queue_reserve(&ctl->n[Q_SHADOW0 + k], out.has_shadow[k]);
-      if (out.has_shadow[k]) {
+      if (k == 0 && !sc.has_dir_light) continue;
+      if (k == 2 && sc.n_lights == 0) continue;
+      bool want = false;
+      float3 dir = f3(0.f), c = f3(0.f);
+      float tmax = kRayMax - kShadowEps;
+      if (active) {
+        float3 wi, le;
+        float pdf;
+        bool valid = true;
+        if (k == 0) {
+          const float2 pd = concentric_disk(smp.next2d());
+          const float3 p = kRayMax * sc.dir_light.dir + sc.dir_disk_radius * (sc.dir_t * pd.x + sc.dir_b * pd.y);
+          dir = normalize(p - shadow_o);
+          wi = fr.to_local(dir);
+          pdf = 1.0f;
+          le = sc.dir_light.le;
+        } else if (k == 1) {
+          // cosine-hemisphere sample of the sky, always drawn (pt.cu:796-857)
+          wi = cosine_hemisphere(smp.next2d());
+          dir = fr.to_world(wi);
+          pdf = abs_cos(wi) / kPi;
+          le = sky_radiance(sc, dir);
+        } else {
+          // uniformly chosen emissive triangle, uniform point on it (pt.cu:282-322, 859-889)
+          const float u1 = smp.next1d();
+          const float2 u2 = smp.next2d();
+          const uint32_t li = min((uint32_t)(u1 * sc.n_lights), sc.n_lights - 1u);
+          const fredholm::AreaLight light = sc.lights[li];
+          const float su = sqrtf(u2.x);
+          const float b0 = 1.0f - su, b1 = u2.y * su;
+          const FaceGeom lg = load_face(sc, light.indices, light.instance_idx);
+          const float3 p = bary3(lg.v0, lg.v1, lg.v2, b0, b1);
+          const float3 nl = bary3(lg.n0, lg.n1, lg.n2, b0, b1);
+          const float2 luv = bary2(lg.t0, lg.t1, lg.t2, b0, b1);
+          const float area = 0.5f * length(cross(lg.v1 - lg.v0, lg.v2 - lg.v0));
+          const float pdf_area = 1.0f / (sc.n_lights * area);
+          const float3 to_l = p - shadow_o;
+          dir = normalize(to_l);
+          const float r = length(to_l);
+          const float cos_l = dot(-dir, nl);
+          valid = cos_l > 0.0f;
+          wi = fr.to_local(dir);
+          pdf = r * r / fabsf(cos_l) * pdf_area;
+          const fredholm::Material& lm = sc.materials[light.material_id];
+          le = TEX ? emission_of(lm, tex, luv) : lm.emission_color;
+          tmax = r - kShadowEps;
+        }
+        if (valid) {
+          float3 f;
+          float pdf_bsdf;
+          bsdf.eval(wi, f, pdf_bsdf);
+          const float mis = pdf / (pdf + pdf_bsdf);
+          const float3 weight = regularize(throughput * mis * f * abs_cos(wi) / pdf);
+          c = weight * le;
+          want = nonzero3(c);  // a zero contribution needs no visibility test (NaN is kept)
+        }
+      }
+      const uint32_t pos = queue_reserve(&ctl->n[Q_SHADOW0 + k], want);
+      if (want) {
         float4* dst = reinterpret_cast<float4*>(wb.shadow[k] + pos);
-        const float4* src = reinterpret_cast<const float4*>(&out.shadow[k]);
-        dst[0] = src[0];
-        dst[1] = src[1];
-        dst[2] = src[2];
+        dst[0] = make_float4(shadow_o.x, shadow_o.y, shadow_o.z, tmax);
+        dst[1] = make_float4(dir.x, dir.y, dir.z, __uint_as_float(slot));
+        dst[2] = make_float4(c.x, c.y, c.z, 0.0f);
       }
     }
-    {
-      const uint32_t pos = queue_reserve(&ctl->n[Q_LIGHT], out.has_light);
-      if (out.has_light) {
-        float4* dst = reinterpret_cast<float4*>(wb.light + pos);
-        const float4* src = reinterpret_cast<const float4*>(&out.light);
-        dst[0] = src[0];
-        dst[1] = src[1];
-        dst[2] = src[2];
+
+    // ---- two independent BSDF samples: 0 = MIS ray towards emitters / sky (pt.cu:892-925),
+    //      1 = path continuation (pt.cu:927-943) ----
+#pragma unroll 1
+    for (int s = 0; s < 2; ++s) {
+      bool want = false;
+      float3 o = f3(0.f), dir = f3(0.f), w = f3(0.f);
+      float pdf = 0.0f, cos_wi = 0.0f;
+      if (active) {
+        const float u1 = smp.next1d();
+        const float2 u2 = smp.next2d();
+        float3 f;
+        const float3 wi = bsdf.sample(u1, u2, f, pdf);
+        dir = fr.to_world(wi);
+        const bool transmitted = dot(dir, n_g) < 0.0f;
+        o = offset_origin(x, transmitted ? -n_g : n_g);
+        cos_wi = abs_cos(wi);
+        if (s == 0) {
+          w = throughput * f * cos_wi / pdf;
+          want = nonzero3(w);
+        } else {
+          throughput *= f * cos_wi / pdf;
+          // raygen loop tail + head of the next iteration (pt.cu:455-471)
+          want = !bad3(throughput) && depth + 1 < wp.max_depth;
+          if (want) {
+            const float p = clampf(luminance(throughput), 0.0f, 1.0f);
+            const float u = smp.next1d();
+            want = !(u >= p);
+            throughput = throughput / p;
+          }
+        }
       }
-    }
-    {
-      const uint32_t pos = queue_reserve(&ctl->n[Q_NEXT], out.continues);
-      if (out.continues) q_out[pos] = slot;
+      if (s == 0) {
+        const uint32_t pos = queue_reserve(&ctl->n[Q_LIGHT], want);
+        if (want) {
+          float4* dst = reinterpret_cast<float4*>(wb.light + pos);
+          dst[0] = make_float4(o.x, o.y, o.z, pdf);
+          dst[1] = make_float4(dir.x, dir.y, dir.z, __uint_as_float(slot));
+          dst[2] = make_float4(w.x, w.y, w.z, cos_wi);
+        }
+      } else {
+        const uint32_t pos = queue_reserve(&ctl->n[Q_NEXT], want);
+        if (want) {
+          wb.ray_o[slot] = make_float4(o.x, o.y, o.z, 0.f);
+          wb.ray_d[slot] = make_float4(dir.x, dir.y, dir.z, 0.f);
+          wb.thr[slot] = make_float4(throughput.x, throughput.y, throughput.z, pack_draws(smp));
+          q_out[pos] = slot;
+        }
+      }
     }
   }
 }
@@ -431,6 +383,7 @@ __global__ void k_advance(WaveControl* ctl)
     ctl->n[Q_SHADOW0] = ctl->n[Q_SHADOW1] = ctl->n[Q_SHADOW2] = 0;
     ctl->n[Q_LIGHT] = 0;
     for (int i = 0; i < 8; ++i) ctl->cursor[i] = 0;
+    for (int i = 0; i < CLS_COUNT; ++i) ctl->n_class[i] = ctl->cursor_class[i] = 0;
   }
 }
 
@@ -439,6 +392,7 @@ __global__ void k_wave_begin(WaveControl* ctl, unsigned long long n_paths)
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     for (int i = 0; i < Q_COUNT; ++i) ctl->n[i] = 0;
     for (int i = 0; i < 8; ++i) ctl->cursor[i] = 0;
+    for (int i = 0; i < CLS_COUNT; ++i) ctl->n_class[i] = ctl->cursor_class[i] = 0;
     ctl->paths += n_paths;
   }
 }
@@ -574,7 +528,7 @@ __global__ void k_test_bsdf(const float* in, uint32_t n, float* out)
   const float3 wo = f3(c[30], c[31], c[32]);
   const bool entering = c[33] != 0.0f;
   const float3 wi = f3(c[34], c[35], c[36]);
-  Closure b;
+  Closure<M_ALL> b;
   b.init(wo, sp, entering);
   float3 f;
   float pdf;
@@ -632,8 +586,6 @@ __global__ void k_test_primary_rays(WaveParams wp, float* out)
   r[5] = d.z;
 }
 
-int g_shade_grid = 0;
-
 int persistent_grid(const void* kernel, int block)
 {
   int dev = 0, sms = 0, per_sm = 0;
@@ -659,10 +611,37 @@ void launch_generate(cudaStream_t s, const WaveParams& wp, const WaveBuffers& wb
   FR_CUDA_LAUNCH_CHECK();
 }
 
-void launch_shade(cudaStream_t s, const WaveParams& wp, const SceneView& sc, const WaveBuffers& wb, uint32_t depth)
+template <uint32_t MASK, bool TEX>
+void launch_shade_t(cudaStream_t s, const WaveParams& wp, const SceneView& sc, const WaveBuffers& wb, uint32_t depth,
+                    int cls)
 {
-  if (g_shade_grid == 0) g_shade_grid = persistent_grid(reinterpret_cast<const void*>(k_shade), kBlock);
-  k_shade<<<g_shade_grid, kBlock, 0, s>>>(wp, sc, wb, depth);
+  static int grid = 0;
+  if (grid == 0) grid = persistent_grid(reinterpret_cast<const void*>(k_shade<MASK, TEX>), kBlock);
+  k_shade<MASK, TEX><<<grid, kBlock, 0, s>>>(wp, sc, wb, depth, cls);
+  FR_CUDA_LAUNCH_CHECK();
+}
+
+void launch_shade(cudaStream_t s, const WaveParams& wp, const SceneView& sc, const WaveBuffers& wb, uint32_t depth,
+                  int cls)
+{
+  switch (cls) {
+    case CLS_DIFFUSE: launch_shade_t<M_DIFFUSE_R, false>(s, wp, sc, wb, depth, cls); break;
+    case CLS_PLASTIC: launch_shade_t<M_SPECULAR | M_DIFFUSE_R, false>(s, wp, sc, wb, depth, cls); break;
+    case CLS_METAL: launch_shade_t<M_METAL | M_DIFFUSE_R, false>(s, wp, sc, wb, depth, cls); break;
+    case CLS_COATED: launch_shade_t<M_COAT | M_SPECULAR | M_DIFFUSE_R, false>(s, wp, sc, wb, depth, cls); break;
+    case CLS_GLASS: launch_shade_t<M_SPECULAR | M_TRANSMISSION | M_DIFFUSE_R, false>(s, wp, sc, wb, depth, cls); break;
+    case CLS_SHEEN: launch_shade_t<M_SHEEN | M_DIFFUSE_R, false>(s, wp, sc, wb, depth, cls); break;
+    case CLS_GENERIC: launch_shade_t<M_ALL, false>(s, wp, sc, wb, depth, cls); break;
+    case CLS_GENERIC_TEX: launch_shade_t<M_ALL, true>(s, wp, sc, wb, depth, cls); break;
+    default: throw std::runtime_error("launch_shade: bad class");
+  }
+}
+
+void launch_miss(cudaStream_t s, const SceneView& sc, const WaveBuffers& wb)
+{
+  static int grid = 0;
+  if (grid == 0) grid = persistent_grid(reinterpret_cast<const void*>(k_miss), kBlock);
+  k_miss<<<grid, kBlock, 0, s>>>(sc, wb);
   FR_CUDA_LAUNCH_CHECK();
 }
 

@@ -53,11 +53,26 @@ __global__ void __launch_bounds__(kBlock) k_trace_closest(SceneView sc, WaveBuff
   const AlphaTest alpha{&sc};
   uint32_t item;
   while (fetch_batch(&ctl->cursor[0], n, item)) {
-    if (item >= n) continue;
-    const uint32_t slot = q[item];
-    const float4 o = wb.ray_o[slot], d = wb.ray_d[slot];
-    const HitRecord h = traverse<false, false>(sc.bvh, f3(o), f3(d), 0.0f, 1e9f, st, alpha, nullptr);
-    wb.hit[slot] = make_float4(h.t, h.u, h.v, __uint_as_float(h.face));
+    int cls = -1;
+    uint32_t slot = 0;
+    if (item < n) {
+      slot = q[item];
+      const float4 o = wb.ray_o[slot], d = wb.ray_d[slot];
+      const HitRecord h = traverse<false, false>(sc.bvh, f3(o), f3(d), 0.0f, 1e9f, st, alpha, nullptr);
+      wb.hit[slot] = make_float4(h.t, h.u, h.v, __uint_as_float(h.face));
+      // a miss only needs work for camera rays (sky seen directly, pt.cu:504-523)
+      cls = h.face != kNoHit ? (int)sc.face_class[h.face] : (depth == 0 ? (int)CLS_MISS : -1);
+    }
+    // sort by material: append the path to the shade queue of the class it hit
+    // (one atomic per class present in the warp)
+    uint32_t todo = __ballot_sync(0xffffffffu, cls >= 0);
+    while (todo) {
+      const int c = __shfl_sync(0xffffffffu, cls, __ffs(todo) - 1);
+      const bool mine = cls == c;
+      const uint32_t pos = queue_reserve(&ctl->n_class[c], mine);
+      if (mine) wb.class_queue[c][pos] = slot;
+      todo &= ~__ballot_sync(0xffffffffu, mine);
+    }
   }
 }
 

@@ -29,6 +29,7 @@ struct SceneView {
   const uint3* indices;            // global vertex ids per face
   const uint32_t* material_ids;    // per face
   const uint32_t* face_submesh;    // per face: submesh == instance == transform index
+  const uint8_t* face_class;       // per face: ShadeClass of its material
   const fredholm::Material* materials;
   const TexView* textures;
   const float* srgb_lut;  // 256-entry sRGB -> linear table
@@ -76,10 +77,28 @@ static_assert(sizeof(LightRay) == 48, "light ray record");
 
 enum QueueId : int { Q_CUR = 0, Q_NEXT, Q_SHADOW0, Q_SHADOW1, Q_SHADOW2, Q_LIGHT, Q_COUNT };
 
+// Material classes of the shade stage.  After closest-hit traversal every path is
+// appended to the queue of the class of the material it hit ("sorting by material"):
+// each class has its own kernel instantiation carrying only the lobes the class needs.
+enum ShadeClass : int {
+  CLS_DIFFUSE = 0,   // Oren-Nayar / Lambert only
+  CLS_PLASTIC,       // specular + diffuse
+  CLS_METAL,         // metalness == 1
+  CLS_COATED,        // coat + specular + diffuse
+  CLS_GLASS,         // specular + transmission + diffuse
+  CLS_SHEEN,         // sheen + diffuse
+  CLS_GENERIC,       // every lobe, no textures
+  CLS_GENERIC_TEX,   // every lobe, textured inputs / bump / normal map
+  CLS_MISS,          // camera rays that left the scene (sky)
+  CLS_COUNT
+};
+
 // device-resident control block: queue sizes, work cursors, statistics
 struct WaveControl {
   uint32_t n[Q_COUNT];
   uint32_t cursor[8];
+  uint32_t n_class[CLS_COUNT];
+  uint32_t cursor_class[CLS_COUNT];
   unsigned long long rays_closest, rays_shadow, rays_light;  // traced rays
   unsigned long long nodes_visited, tris_tested;             // only in stats builds
   unsigned long long paths;
@@ -95,6 +114,7 @@ struct WaveBuffers {
   float4* aov1;   // [n_slots] normal xyz, texcoord.x
   float4* aov2;   // [n_slots] albedo xyz, texcoord.y
   uint32_t* queue[2];       // [n_slots] path slots of live radiance rays (ping-pong)
+  uint32_t* class_queue[CLS_COUNT];  // [n_slots] each: paths to shade, by material class
   ShadowRay* shadow[3];     // [n_slots] directional / sky / area-light NEE rays
   LightRay* light;          // [n_slots] MIS rays
   WaveControl* ctl;

@@ -15,7 +15,9 @@ enum FilmMode : int {
 // shade.cu
 void launch_wave_begin(cudaStream_t s, const WaveBuffers& wb, unsigned long long n_paths);
 void launch_generate(cudaStream_t s, const WaveParams& wp, const WaveBuffers& wb);
-void launch_shade(cudaStream_t s, const WaveParams& wp, const SceneView& sc, const WaveBuffers& wb, uint32_t depth);
+void launch_shade(cudaStream_t s, const WaveParams& wp, const SceneView& sc, const WaveBuffers& wb, uint32_t depth,
+                  int cls);
+void launch_miss(cudaStream_t s, const SceneView& sc, const WaveBuffers& wb);
 void launch_advance(cudaStream_t s, const WaveBuffers& wb);
 void launch_film(cudaStream_t s, const WaveParams& wp, const WaveBuffers& wb, const fredholm::RenderLayer& layers,
                  int film_mode);
