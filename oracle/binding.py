@@ -273,3 +273,23 @@ def camera_walk(origin, d_phi, d_theta, movement, dt):
     lib().orc_camera_walk(_f(_f32(origin, 3)), C.c_float(d_phi), C.c_float(d_theta), C.c_int(movement),
                           C.c_float(dt), _f(out))
     return out
+
+
+# ---- the reference's own post-process kernels compiled with nvcc (GPU box only) ----------
+PP_LIB_PATH = os.path.join(_HERE, "_ref", "libpostprocess_ref.so")
+_pp = None
+
+
+def post_process_ref_available():
+    return os.path.exists(PP_LIB_PATH)
+
+
+def post_process_ref_lib():
+    global _pp
+    if _pp is None:
+        _pp = C.CDLL(PP_LIB_PATH)
+        _pp.ppr_last_error.restype = C.c_char_p
+        _pp.ppr_post_process.argtypes = [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float,
+                                         C.c_float, _vp]
+        _pp.ppr_tone_mapping.argtypes = [_vp, C.c_int, C.c_int, C.c_float, C.c_float, _vp]
+    return _pp

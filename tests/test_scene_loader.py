@@ -1,0 +1,95 @@
+"""Scene ingestion on the boundary (Scene::load_model, scene.cpp:103-443): our own .obj/.mtl
+parser must produce exactly the flat arrays the reference's tinyobjloader-based loader
+produces (vertex de-duplication order, default normals / texcoords, MTL -> Material incl. the
+custom keys and the reference's quirks).  Host only -- no GPU needed."""
+import os
+
+import numpy as np
+import pytest
+
+from fredholm_b200 import api, scenes
+
+FIELDS = ("vertices", "normals", "texcoords", "indices", "material_ids", "instance_ids", "submesh_offsets",
+          "submesh_n_faces", "transforms")
+
+
+def load_both(oracle_mod, path):
+    sc = api.Scene()
+    sc.load_model(path)
+    ours = sc.arrays()
+    sc.close()
+    o = oracle_mod.Oracle()
+    o.load_scene(path)
+    return ours, o.get_loaded_scene()
+
+
+def assert_same(a, b):
+    for k in FIELDS:
+        assert np.array_equal(getattr(a, k), getattr(b, k)), k
+    assert a.materials.tobytes() == b.materials.tobytes()
+    assert len(a.textures) == len(b.textures)
+
+
+@pytest.mark.parametrize("with_attributes", [True, False])
+def test_obj_cornell(oracle_mod, tmp_path, with_attributes):
+    p = scenes.write_obj(scenes.cornell_box(), str(tmp_path), "cornell", with_attributes=with_attributes)
+    ours, ref = load_both(oracle_mod, p)
+    assert_same(ours, ref)
+    assert ours.n_faces == 32 and len(ours.submesh_offsets) == 4
+    # emissive material came through Ke (light list is every emissive face, renderer.h:388-402)
+    assert (ours.materials["emission_color"].sum(axis=1) > 0).sum() == 1
+
+
+def test_obj_standard_surface(oracle_mod, tmp_path):
+    s = scenes.standard_surface_scene(16, 8, sphere_res=(8, 4))
+    p = scenes.write_obj(s, str(tmp_path), "std")
+    ours, ref = load_both(oracle_mod, p)
+    assert_same(ours, ref)
+    # custom MTL keys round-trip (scene.cpp:251-312)
+    for k in ("sheen", "coat", "metalness", "transmission", "specular_roughness", "diffuse_roughness"):
+        assert np.allclose(ours.materials[k], s.materials[k], atol=1e-6), k
+
+
+def test_obj_quirks(oracle_mod, tmp_path):
+    """Hand-written file: negative indices, polygons (fan triangulation), missing vt/vn,
+    comments, `Pcr`, `d`, several usemtl in one object, object without a material."""
+    (tmp_path / "q.mtl").write_text(
+        "# comment\nnewmtl a\nKd 0.1 0.2 0.3\nKs 0.5 0.5 0.5\nPr 0.35\nPm 0.25\nPc 0.8\nPcr 0.15\nd 0.25\n"
+        "Tf 0.9 0.8 0.7\nKe 0 0 0\n\nnewmtl b\nKd 1 1 1\nKe 2 3 4\nsheen 0.5\nsheen_color 0.1 0.2 0.3\n"
+        "sheen_roughness 0.7\nsubsurface 0.2\nsubsurface_color 0.3 0.4 0.5\nthin_walled 1\ndiffuse 0.75\n"
+        "diffuse_roughness 0.4\n")
+    (tmp_path / "q.obj").write_text(
+        "mtllib q.mtl\n# a quad, a pentagon and a triangle\n"
+        "v 0 0 0\nv 1 0 0\nv 1 1 0\nv 0 1 0\nv 0.5 1.5 0\nv 0 0 1\nv 1 0 1\nv 0 1 1\n"
+        "vn 0 0 1\nvt 0 0\nvt 1 0\nvt 1 1\nvt 0 1\n"
+        "o first\nusemtl a\nf 1/1/1 2/2/1 3/3/1 4/4/1\nusemtl b\nf 1 2 3 5 4\n"
+        "o second\nusemtl a\nf -3//1 -2//1 -1//1\nf 6/1 7/2 8/3\n")
+    ours, ref = load_both(oracle_mod, str(tmp_path / "q.obj"))
+    assert_same(ours, ref)
+    assert ours.n_faces == 2 + 3 + 2
+    a = ours.materials[0]
+    assert np.isclose(a["transmission"], 0.75) and np.isclose(a["coat"], 0.8)
+
+
+def test_invalid_scene(tmp_path):
+    sc = api.Scene()
+    with pytest.raises(api.FredholmError):
+        sc.load_model(str(tmp_path / "missing.obj"))
+    (tmp_path / "x.ply").write_text("ply\n")
+    with pytest.raises(api.FredholmError):
+        sc.load_model(str(tmp_path / "x.ply"))   # reference: std::runtime_error("invalid scene")
+    sc.close()
+
+
+def test_append_without_clear(oracle_mod, tmp_path):
+    p = scenes.write_obj(scenes.cornell_box(), str(tmp_path), "c")
+    sc = api.Scene()
+    sc.load_model(p)
+    sc.load_model(p, clear=False)
+    a = sc.arrays()
+    sc.close()
+    o = oracle_mod.Oracle()
+    o.load_scene(p)
+    o.load_scene(p, clear=False)
+    assert_same(a, o.get_loaded_scene())
+    assert a.n_faces == 64
