@@ -152,7 +152,8 @@ constexpr int kLocalStack = 36;
 struct TravStack {
   uint2* smem;  // &smem_stack[0][thread]
   int stride;   // threads per block
-  uint2 local[kLocalStack];
+  uint2* local;  // [kLocalStack] thread-local overflow, declared by the caller so that the rest of
+                 // the traversal state stays in registers
   int sp;
   FR_D void push(const uint2& e)
   {
@@ -179,114 +180,228 @@ struct NoAnyHit {
   FR_D bool operator()(uint32_t, float, float) const { return true; }
 };
 
+// Per-lane traversal state machine, driven warp-synchronously by trace_queue().
+//
+// A lane owns one ray.  Its work is split into two phases that the WARP schedules:
+//   node phase      pop one child of the current node group, fetch the 80-byte node, test
+//                   its 8 quantised boxes (~280 SASS instructions, ~90 % of lanes busy)
+//   triangle phase  test ONE pending leaf triangle (watertight, ~100 instructions)
+// Testing a node's leaf triangles right away (the textbook while-while loop) ran the
+// triangle code with ~3 of 32 lanes active and cost as many issue slots as all node tests
+// together (profiles/r1c_trace_closest_source.txt).  Instead a lane parks the triangle
+// group it found (two slots) and keeps descending; the warp runs a triangle phase only when
+// enough lanes have a triangle pending (or nothing else can make progress), so the
+// triangle code runs with most lanes active.  The order of triangle tests does not change
+// the result: closest hit is a minimum with a fixed tie rule, any-hit only reports
+// occlusion.
+//
 // Closest hit (ANY = false) or first accepted hit (ANY = true).
 // Tie rule on exactly equal t: lower global face index wins (as in the oracle).
-template <bool ANY, bool COUNT, typename AnyHit>
-FR_D HitRecord traverse(const BvhView& bvh, const float3& o, const float3& d, float tmin, float tmax,
-                        TravStack& st, const AnyHit& anyhit, TraceCounters* cnt)
-{
+struct Traverser {
+  float3 o;
+  RayShear sh;
+  float3 idir;  // 1 / d (components of |d| < tiny replaced, box tests only)
+  uint32_t octinv;
+  float tmin;
   HitRecord best;
-  best.t = tmax;
-  best.u = best.v = 0.0f;
-  best.face = kNoHit;
+  uint2 ngroup;   // current node group: x = child base, y = hit bits (31..24) | imask; y == 0: none
+  uint2 tgroup;   // pending triangles: x = triangle base, y = 24-bit mask
+  uint2 tgroup2;  // second parking slot
+  TravStack st;
 
-  const RayShear sh = make_shear(d);
-  // box tests are conservative: guard against 0 * inf and widen by a few ulps
-  const float tiny = 1e-30f;
-  const float3 ds = f3(fabsf(d.x) > tiny ? d.x : copysignf(tiny, d.x),
-                       fabsf(d.y) > tiny ? d.y : copysignf(tiny, d.y),
-                       fabsf(d.z) > tiny ? d.z : copysignf(tiny, d.z));
-  const float3 idir = f3(1.0f / ds.x, 1.0f / ds.y, 1.0f / ds.z);
-  const uint32_t octinv = (d.x >= 0.0f ? 1u : 0u) | (d.y >= 0.0f ? 2u : 0u) | (d.z >= 0.0f ? 4u : 0u);
-  const uint32_t octinv4 = octinv * 0x01010101u;
-  constexpr float kFar = 1.0000005f, kNear = 0.9999995f;
+  FR_D void begin(const float3& org, const float3& d, float t_min, float t_max)
+  {
+    o = org;
+    tmin = t_min;
+    best.t = t_max;
+    best.u = best.v = 0.0f;
+    best.face = kNoHit;
+    sh = make_shear(d);
+    // box tests are conservative: guard against 0 * inf and widen by a few ulps
+    const float tiny = 1e-20f;
+    const float3 ds = f3(fabsf(d.x) > tiny ? d.x : copysignf(tiny, d.x),
+                         fabsf(d.y) > tiny ? d.y : copysignf(tiny, d.y),
+                         fabsf(d.z) > tiny ? d.z : copysignf(tiny, d.z));
+    idir = f3(1.0f / ds.x, 1.0f / ds.y, 1.0f / ds.z);
+    octinv = (d.x >= 0.0f ? 1u : 0u) | (d.y >= 0.0f ? 2u : 0u) | (d.z >= 0.0f ? 4u : 0u);
+    st.sp = 0;
+    ngroup = make_uint2(0u, 0x80000000u);
+    tgroup = make_uint2(0u, 0u);
+    tgroup2 = make_uint2(0u, 0u);
+  }
 
-  st.sp = 0;
-  uint2 ngroup = make_uint2(0u, 0x80000000u);
-  uint2 tgroup = make_uint2(0u, 0u);
+  FR_D bool has_triangles() const { return tgroup.y != 0u; }
+  // node work available and a free slot to park the triangles it may produce
+  FR_D bool can_descend() const { return ngroup.y != 0u && tgroup2.y == 0u; }
+  FR_D bool finished() const { return ngroup.y == 0u && tgroup.y == 0u; }
 
-  for (;;) {
-    if (ngroup.y > 0x00ffffffu) {
-      const uint32_t hits_imask = ngroup.y;
-      const uint32_t bit = 31u - __clz(hits_imask);
-      ngroup.y &= ~(1u << bit);
-      if (ngroup.y > 0x00ffffffu) st.push(ngroup);
-      const uint32_t slot = (bit ^ octinv) & 7u;
-      const uint32_t rel = __popc(hits_imask & ~(0xffffffffu << slot));
-      const float4* np = bvh.nodes + 5ull * (ngroup.x + rel);
-      const float4 n0 = __ldg(np + 0), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3),
-                   n4 = __ldg(np + 4);
-      if (COUNT) cnt->nodes++;
-      const uint32_t ew = __float_as_uint(n0.w);
-      const float sx = __uint_as_float((ew & 0xffu) << 23);
-      const float sy = __uint_as_float(((ew >> 8) & 0xffu) << 23);
-      const float sz = __uint_as_float(((ew >> 16) & 0xffu) << 23);
-      const float ax = sx * idir.x, ay = sy * idir.y, az = sz * idir.z;
-      const float bx = (n0.x - o.x) * idir.x, by = (n0.y - o.y) * idir.y, bz = (n0.z - o.z) * idir.z;
-      uint32_t hitmask = 0;
+  template <bool COUNT>
+  FR_D void node_phase(const BvhView& bvh, TraceCounters* cnt)
+  {
+    constexpr float kFar = 1.0000005f, kNear = 0.9999995f;
+    const uint32_t hits_imask = ngroup.y;
+    const uint32_t bit = 31u - __clz(hits_imask);
+    ngroup.y &= ~(1u << bit);  // what is left of this group (pushed below if the child has inner hits)
+    const uint32_t slot = (bit ^ octinv) & 7u;
+    const uint32_t rel = __popc(hits_imask & ~(0xffffffffu << slot));
+    const float4* np = bvh.nodes + 5ull * (ngroup.x + rel);
+    const float4 n0 = __ldg(np + 0), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3),
+                 n4 = __ldg(np + 4);
+    if (COUNT) cnt->nodes++;
+    const uint32_t ew = __float_as_uint(n0.w);
+    const float sx = __uint_as_float((ew & 0xffu) << 23);
+    const float sy = __uint_as_float(((ew >> 8) & 0xffu) << 23);
+    const float sz = __uint_as_float(((ew >> 16) & 0xffu) << 23);
+    const float ax = sx * idir.x, ay = sy * idir.y, az = sz * idir.z;
+    const float bx = (n0.x - o.x) * idir.x, by = (n0.y - o.y) * idir.y, bz = (n0.z - o.z) * idir.z;
+    const bool negx = !(octinv & 1u), negy = !(octinv & 2u), negz = !(octinv & 4u);
+    const uint32_t octinv4 = octinv * 0x01010101u;
+    const float tnear0 = tmin, tfar0 = best.t;
+    uint32_t hitmask = 0;
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        const uint32_t meta4 = __float_as_uint(half == 0 ? n1.z : n1.w);
-        const uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
-        const uint32_t inner_mask4 = sign_extend_s8x4(is_inner4 << 3);
-        const uint32_t bit_index4 = (meta4 ^ (octinv4 & inner_mask4)) & 0x1f1f1f1fu;
-        const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
-        const uint32_t qlox = __float_as_uint(half == 0 ? n2.x : n2.y);
-        const uint32_t qloy = __float_as_uint(half == 0 ? n2.z : n2.w);
-        const uint32_t qloz = __float_as_uint(half == 0 ? n3.x : n3.y);
-        const uint32_t qhix = __float_as_uint(half == 0 ? n3.z : n3.w);
-        const uint32_t qhiy = __float_as_uint(half == 0 ? n4.x : n4.y);
-        const uint32_t qhiz = __float_as_uint(half == 0 ? n4.z : n4.w);
-        const uint32_t nx = d.x < 0.0f ? qhix : qlox, fx = d.x < 0.0f ? qlox : qhix;
-        const uint32_t ny = d.y < 0.0f ? qhiy : qloy, fy = d.y < 0.0f ? qloy : qhiy;
-        const uint32_t nz = d.z < 0.0f ? qhiz : qloz, fz = d.z < 0.0f ? qloz : qhiz;
+    for (int half = 0; half < 2; ++half) {
+      const uint32_t meta4 = __float_as_uint(half == 0 ? n1.z : n1.w);
+      const uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
+      const uint32_t inner_mask4 = sign_extend_s8x4(is_inner4 << 3);
+      const uint32_t bit_index4 = (meta4 ^ (octinv4 & inner_mask4)) & 0x1f1f1f1fu;
+      const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
+      const uint32_t qlox = __float_as_uint(half == 0 ? n2.x : n2.y);
+      const uint32_t qloy = __float_as_uint(half == 0 ? n2.z : n2.w);
+      const uint32_t qloz = __float_as_uint(half == 0 ? n3.x : n3.y);
+      const uint32_t qhix = __float_as_uint(half == 0 ? n3.z : n3.w);
+      const uint32_t qhiy = __float_as_uint(half == 0 ? n4.x : n4.y);
+      const uint32_t qhiz = __float_as_uint(half == 0 ? n4.z : n4.w);
+      const uint32_t nx = negx ? qhix : qlox, fx = negx ? qlox : qhix;
+      const uint32_t ny = negy ? qhiy : qloy, fy = negy ? qloy : qhiy;
+      const uint32_t nz = negz ? qhiz : qloz, fz = negz ? qloz : qhiz;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float t0x = fmaf(byte_f(nx, j), ax, bx), t1x = fmaf(byte_f(fx, j), ax, bx);
-          const float t0y = fmaf(byte_f(ny, j), ay, by), t1y = fmaf(byte_f(fy, j), ay, by);
-          const float t0z = fmaf(byte_f(nz, j), az, bz), t1z = fmaf(byte_f(fz, j), az, bz);
-          const float cnear = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, tmin)) * kNear;
-          const float cfar = fminf(fminf(t1x, t1y), fminf(t1z, best.t)) * kFar;
-          if (cnear <= cfar) {
-            const uint32_t cb = (child_bits4 >> (8 * j)) & 0xffu;
-            const uint32_t bi = (bit_index4 >> (8 * j)) & 0xffu;
-            hitmask |= cb << bi;
-          }
+      for (int j = 0; j < 4; ++j) {
+        const float t0x = fmaf(byte_f(nx, j), ax, bx), t1x = fmaf(byte_f(fx, j), ax, bx);
+        const float t0y = fmaf(byte_f(ny, j), ay, by), t1y = fmaf(byte_f(fy, j), ay, by);
+        const float t0z = fmaf(byte_f(nz, j), az, bz), t1z = fmaf(byte_f(fz, j), az, bz);
+        const float cnear = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, tnear0)) * kNear;
+        const float cfar = fminf(fminf(t1x, t1y), fminf(t1z, tfar0)) * kFar;
+        if (cnear <= cfar) {
+          const uint32_t cb = (child_bits4 >> (8 * j)) & 0xffu;
+          const uint32_t bi = (bit_index4 >> (8 * j)) & 0xffu;
+          hitmask |= cb << bi;
         }
       }
+    }
+    // inner children hit: descend into this node's group, the rest of the parent's group
+    // goes to the stack; none: carry on with the rest of the group, or resume from the stack
+    if (hitmask & 0xff000000u) {
+      if (ngroup.y > 0x00ffffffu) st.push(ngroup);
       ngroup.x = __float_as_uint(n1.x);
       ngroup.y = (hitmask & 0xff000000u) | (ew >> 24);
-      tgroup.x = __float_as_uint(n1.y);
-      tgroup.y = hitmask & 0x00ffffffu;
-    } else {
-      tgroup = ngroup;
-      ngroup = make_uint2(0u, 0u);
+    } else if (ngroup.y <= 0x00ffffffu) {
+      ngroup = st.sp > 0 ? st.pop() : make_uint2(0u, 0u);
     }
-
-    while (tgroup.y != 0u) {
-      const uint32_t bit = __ffs(tgroup.y) - 1u;
-      tgroup.y &= tgroup.y - 1u;
-      const float4* tp = bvh.tris + 3ull * (tgroup.x + bit);
-      const float4 v0 = __ldg(tp + 0), v1 = __ldg(tp + 1), v2 = __ldg(tp + 2);
-      if (COUNT) cnt->tris++;
-      float t, u, v;
-      if (!watertight_hit(sh, o, v0, v1, v2, tmin, best.t, best.face != kNoHit, t, u, v)) continue;
-      const uint32_t face = __float_as_uint(v0.w);
-      if (t == best.t && best.face != kNoHit && face > best.face) continue;
-      if ((__float_as_uint(v1.w) & 1u) && !anyhit(face, u, v)) continue;
-      best.t = t;
-      best.u = u;
-      best.v = v;
-      best.face = face;
-      if (ANY) return best;
-    }
-
-    if (ngroup.y <= 0x00ffffffu) {
-      if (st.sp == 0) break;
-      ngroup = st.pop();
+    // park the leaf triangles this node produced
+    const uint32_t tmask = hitmask & 0x00ffffffu;
+    if (tmask) {
+      const uint2 tg = make_uint2(__float_as_uint(n1.y), tmask);
+      if (tgroup.y == 0u)
+        tgroup = tg;
+      else
+        tgroup2 = tg;
     }
   }
-  return best;
+
+  // tests ONE pending triangle; returns true if an ANY ray found its hit
+  template <bool ANY, bool COUNT, typename AnyHit>
+  FR_D bool triangle_phase(const BvhView& bvh, const AnyHit& anyhit, TraceCounters* cnt)
+  {
+    const uint32_t bit = __ffs(tgroup.y) - 1u;
+    tgroup.y &= tgroup.y - 1u;
+    const float4* tp = bvh.tris + 3ull * (tgroup.x + bit);
+    const float4 v0 = __ldg(tp + 0), v1 = __ldg(tp + 1), v2 = __ldg(tp + 2);
+    if (tgroup.y == 0u) {
+      tgroup = tgroup2;
+      tgroup2 = make_uint2(0u, 0u);
+    }
+    if (COUNT) cnt->tris++;
+    float t, u, v;
+    if (!watertight_hit(sh, o, v0, v1, v2, tmin, best.t, best.face != kNoHit, t, u, v)) return false;
+    const uint32_t face = __float_as_uint(v0.w);
+    if (t == best.t && best.face != kNoHit && face > best.face) return false;
+    if ((__float_as_uint(v1.w) & 1u) && !anyhit(face, u, v)) return false;
+    best.t = t;
+    best.u = u;
+    best.v = v;
+    best.face = face;
+    return ANY;
+  }
+};
+
+// Persistent-warp queue driver (trace.cu kernels).  Every lane owns one ray; the warp
+// iterates { vote, triangle phase, node phase } fully converged at the top of each
+// iteration:
+//  * lane refill (Aila & Laine 2009 "dynamic fetch"): when at least `refill_lanes` lanes are
+//    idle the finished rays are retired (Policy::retire, whole warp converged so it can use
+//    warp-aggregated queue appends) and the idle lanes fetch new items with ONE atomic on the
+//    queue cursor; once the queue is exhausted the warp drains;
+//  * triangle phase when at least `tri_lanes` lanes have a triangle pending, or when no lane
+//    can descend.
+//
+// Policy interface:
+//   void load(uint32_t item, float3& o, float3& d, float& tmin, float& tmax)  (lane-local payload)
+//   void retire(bool has_result, const HitRecord& h, const TraceCounters&)    all 32 lanes together
+//   anyhit()                                                                  alpha-test functor
+template <bool ANY, bool COUNT, typename Policy>
+FR_D void trace_queue(const BvhView& bvh, Policy& pol, uint32_t* cursor, uint32_t n, uint2* smem_column,
+                      int stride, int refill_lanes, int tri_lanes)
+{
+  uint2 overflow[kLocalStack];
+  Traverser tr;
+  tr.st.smem = smem_column;
+  tr.st.stride = stride;
+  tr.st.local = overflow;
+  tr.st.sp = 0;
+  tr.ngroup = tr.tgroup = tr.tgroup2 = make_uint2(0u, 0u);
+  TraceCounters cnt{0u, 0u};
+  const uint32_t lane = threadIdx.x & 31u;
+  bool have = false;      // lane is traversing a ray
+  bool finished = false;  // lane holds a finished ray that has not been retired yet
+  bool exhausted = false;
+  for (;;) {
+    const uint32_t idle = __ballot_sync(0xffffffffu, !have);
+    if (idle == 0xffffffffu || (!exhausted && __popc(idle) >= refill_lanes)) {
+      pol.retire(finished, tr.best, cnt);
+      finished = false;
+      if (!exhausted) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(cursor, (uint32_t)__popc(idle));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        const uint32_t item = base + __popc(idle & ((1u << lane) - 1u));
+        if (!have && item < n) {
+          float3 o, d;
+          float tmin, tmax;
+          pol.load(item, o, d, tmin, tmax);
+          tr.begin(o, d, tmin, tmax);
+          if (COUNT) cnt.nodes = cnt.tris = 0u;
+          have = true;
+        }
+        exhausted = base + __popc(idle) >= n;
+      }
+      if (__ballot_sync(0xffffffffu, have) == 0u) break;
+    }
+    // ---- vote ----
+    const bool want_tri = have && tr.has_triangles();
+    const uint32_t tri_votes = __ballot_sync(0xffffffffu, want_tri);
+    const uint32_t node_votes = __ballot_sync(0xffffffffu, have && tr.can_descend());
+    bool done = false;
+    if (tri_votes != 0u && (__popc(tri_votes) >= tri_lanes || node_votes == 0u)) {
+      if (want_tri) done = tr.template triangle_phase<ANY, COUNT>(bvh, pol.anyhit(), &cnt);
+      __syncwarp();
+    }
+    if (have && !done && tr.can_descend()) tr.template node_phase<COUNT>(bvh, &cnt);
+    if (have && (done || tr.finished())) {
+      have = false;
+      finished = true;
+    }
+    __syncwarp();
+  }
 }
 
 }  // namespace frd

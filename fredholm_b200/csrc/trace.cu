@@ -8,6 +8,9 @@
 //                                      pt.cu:111-123, 531-543, 952-998) with the emitter
 //                                      record and MIS weight resolved in the epilogue
 // All three honour the reference's alpha cut-out (any-hit programs, pt.cu:545-678).
+#include <algorithm>
+#include <cstdlib>
+
 #include "cuda_util.h"
 #include "queue.cuh"
 #include "surface.cuh"
@@ -37,95 +40,127 @@ struct AlphaTest {
   }
 };
 
-#define FR_DECLARE_STACK()                                  \
-  __shared__ uint2 s_stack[kSmemStack * kBlock];            \
-  TravStack st;                                             \
-  st.smem = s_stack + threadIdx.x;                          \
-  st.stride = kBlock;                                       \
-  st.sp = 0
+#define FR_DECLARE_STACK()                       \
+  __shared__ uint2 s_stack[kSmemStack * kBlock]; \
+  uint2* const stack_column = s_stack + threadIdx.x
 
-__global__ void __launch_bounds__(kBlock) k_trace_closest(SceneView sc, WaveBuffers wb, uint32_t depth)
-{
-  FR_DECLARE_STACK();
-  WaveControl* ctl = wb.ctl;
-  const uint32_t n = ctl->n[Q_CUR];
-  const uint32_t* q = wb.queue[depth & 1u];
-  const AlphaTest alpha{&sc};
-  uint32_t item;
-  while (fetch_batch(&ctl->cursor[0], n, item)) {
+// ---- radiance rays: closest hit, then "sort by material" ---------------------------------
+struct ClosestPolicy {
+  const SceneView& sc;
+  const WaveBuffers& wb;
+  const uint32_t* q;
+  uint32_t depth;
+  uint32_t slot;
+  FR_D AlphaTest anyhit() const { return AlphaTest{&sc}; }
+  FR_D void load(uint32_t item, float3& o, float3& d, float& tmin, float& tmax)
+  {
+    slot = q[item];
+    const float4 ro = wb.ray_o[slot], rd = wb.ray_d[slot];
+    o = f3(ro);
+    d = f3(rd);
+    tmin = 0.0f;
+    tmax = 1e9f;
+  }
+  FR_D void retire(bool has, const HitRecord& h, const TraceCounters&)
+  {
     int cls = -1;
-    uint32_t slot = 0;
-    if (item < n) {
-      slot = q[item];
-      const float4 o = wb.ray_o[slot], d = wb.ray_d[slot];
-      const HitRecord h = traverse<false, false>(sc.bvh, f3(o), f3(d), 0.0f, 1e9f, st, alpha, nullptr);
+    if (has) {
       wb.hit[slot] = make_float4(h.t, h.u, h.v, __uint_as_float(h.face));
       // a miss only needs work for camera rays (sky seen directly, pt.cu:504-523)
       cls = h.face != kNoHit ? (int)sc.face_class[h.face] : (depth == 0 ? (int)CLS_MISS : -1);
     }
-    // sort by material: append the path to the shade queue of the class it hit
-    // (one atomic per class present in the warp)
+    // append the path to the shade queue of the class it hit (one atomic per class
+    // present among the retiring lanes)
     uint32_t todo = __ballot_sync(0xffffffffu, cls >= 0);
     while (todo) {
       const int c = __shfl_sync(0xffffffffu, cls, __ffs(todo) - 1);
       const bool mine = cls == c;
-      const uint32_t pos = queue_reserve(&ctl->n_class[c], mine);
+      const uint32_t pos = queue_reserve(&wb.ctl->n_class[c], mine);
       if (mine) wb.class_queue[c][pos] = slot;
       todo &= ~__ballot_sync(0xffffffffu, mine);
     }
   }
-}
+};
 
-__global__ void __launch_bounds__(kBlock) k_trace_shadow(SceneView sc, WaveBuffers wb, int which)
+__global__ void __launch_bounds__(kBlock, 8) k_trace_closest(SceneView sc, WaveBuffers wb, uint32_t depth, int refill, int tri_lanes)
 {
   FR_DECLARE_STACK();
-  WaveControl* ctl = wb.ctl;
-  const uint32_t n = ctl->n[Q_SHADOW0 + which];
-  const float4* q = reinterpret_cast<const float4*>(wb.shadow[which]);
-  const AlphaTest alpha{&sc};
-  uint32_t item;
-  while (fetch_batch(&ctl->cursor[2 + which], n, item)) {
-    if (item >= n) continue;
+  ClosestPolicy pol{sc, wb, wb.queue[depth & 1u], depth, 0u};
+  trace_queue<false, false>(sc.bvh, pol, &wb.ctl->cursor[0], wb.ctl->n[Q_CUR], stack_column, kBlock, refill, tri_lanes);
+}
+
+// ---- visibility rays: any hit; an unoccluded ray adds its contribution ----------------------
+struct ShadowPolicy {
+  const SceneView& sc;
+  const WaveBuffers& wb;
+  const float4* q;
+  uint32_t path;
+  float3 c;
+  FR_D AlphaTest anyhit() const { return AlphaTest{&sc}; }
+  FR_D void load(uint32_t item, float3& o, float3& d, float& tmin, float& tmax)
+  {
     const float4 r0 = q[3ull * item], r1 = q[3ull * item + 1], r2 = q[3ull * item + 2];
-    const HitRecord h =
-        traverse<true, false>(sc.bvh, f3(r0), f3(r1), 0.0f, r0.w, st, alpha, nullptr);
-    if (h.face == kNoHit) {
+    o = f3(r0);
+    d = f3(r1);
+    tmin = 0.0f;
+    tmax = r0.w;
+    path = __float_as_uint(r1.w);
+    c = f3(r2);
+  }
+  FR_D void retire(bool has, const HitRecord& h, const TraceCounters&)
+  {
+    if (has && h.face == kNoHit) {
       // one ray per path and kernel: plain read-modify-write, deterministic order
-      const uint32_t path = __float_as_uint(r1.w);
       float4 L = wb.L[path];
-      L.x += r2.x;
-      L.y += r2.y;
-      L.z += r2.z;
+      L.x += c.x;
+      L.y += c.y;
+      L.z += c.z;
       wb.L[path] = L;
     }
   }
-}
+};
 
-__global__ void __launch_bounds__(kBlock) k_trace_light(SceneView sc, WaveBuffers wb)
+__global__ void __launch_bounds__(kBlock, 8) k_trace_shadow(SceneView sc, WaveBuffers wb, int which, int refill, int tri_lanes)
 {
   FR_DECLARE_STACK();
-  WaveControl* ctl = wb.ctl;
-  const uint32_t n = ctl->n[Q_LIGHT];
-  const float4* q = reinterpret_cast<const float4*>(wb.light);
-  const AlphaTest alpha{&sc};
-  uint32_t item;
-  while (fetch_batch(&ctl->cursor[5], n, item)) {
-    if (item >= n) continue;
+  ShadowPolicy pol{sc, wb, reinterpret_cast<const float4*>(wb.shadow[which]), 0u, f3(0.f)};
+  trace_queue<true, false>(sc.bvh, pol, &wb.ctl->cursor[2 + which], wb.ctl->n[Q_SHADOW0 + which], stack_column, kBlock,
+                           refill, tri_lanes);
+}
+
+// ---- MIS rays: closest hit, emitter record + MIS weight in the epilogue -----------------------
+struct LightPolicy {
+  const SceneView& sc;
+  const WaveBuffers& wb;
+  const float4* q;
+  float3 o, d, w;
+  float pdf_bsdf, cos_wi;
+  uint32_t path;
+  FR_D AlphaTest anyhit() const { return AlphaTest{&sc}; }
+  FR_D void load(uint32_t item, float3& ro, float3& rd, float& tmin, float& tmax)
+  {
     const float4 r0 = q[3ull * item], r1 = q[3ull * item + 1], r2 = q[3ull * item + 2];
-    const float3 o = f3(r0), d = f3(r1);
-    const HitRecord h = traverse<false, false>(sc.bvh, o, d, 0.0f, 1e9f, st, alpha, nullptr);
-    const float pdf_bsdf = r0.w;
+    ro = o = f3(r0);
+    rd = d = f3(r1);
+    tmin = 0.0f;
+    tmax = 1e9f;
+    pdf_bsdf = r0.w;
+    path = __float_as_uint(r1.w);
+    w = f3(r2);
+    cos_wi = r2.w;
+  }
+  FR_D void retire(bool has, const HitRecord& h, const TraceCounters&)
+  {
+    if (!has) return;
     float3 le = f3(0.0f);
-    float pdf_light;
+    float pdf_light = cos_wi / kPi;
     bool contributes = true;
     if (h.face == kNoHit) {
       // __miss__light: environment radiance, cosine pdf of the sky NEE strategy
       le = sky_radiance(sc, d);
-      pdf_light = r2.w / kPi;
     } else {
       // __closesthit__light: an emitter record only for emissive, front-facing faces
       const fredholm::Material& m = sc.materials[sc.material_ids[h.face]];
-      pdf_light = r2.w / kPi;
       contributes = false;
       if (is_emissive(m)) {
         const FaceGeom g = load_face(sc, sc.indices[h.face], sc.face_submesh[h.face]);
@@ -147,48 +182,103 @@ __global__ void __launch_bounds__(kBlock) k_trace_light(SceneView sc, WaveBuffer
     }
     if (contributes) {
       const float mis = pdf_bsdf / (pdf_bsdf + pdf_light);
-      const float3 w = clamp3(f3(r2.x * mis, r2.y * mis, r2.z * mis), 0.0f, 1.0f);
-      const uint32_t path = __float_as_uint(r1.w);
+      const float3 ww = clamp3(f3(w.x * mis, w.y * mis, w.z * mis), 0.0f, 1.0f);
       float4 L = wb.L[path];
-      L.x += w.x * le.x;
-      L.y += w.y * le.y;
-      L.z += w.z * le.z;
+      L.x += ww.x * le.x;
+      L.y += ww.y * le.y;
+      L.z += ww.z * le.z;
       wb.L[path] = L;
     }
   }
+};
+
+// ANY = true when the scene has no emissive face at all (n_lights == 0, the light list holds
+// every emissive face): then a MIS ray contributes only if it leaves the scene, so the first
+// accepted hit settles it and the closest one need not be found.
+template <bool ANY>
+__global__ void __launch_bounds__(kBlock, 8) k_trace_light(SceneView sc, WaveBuffers wb, int refill, int tri_lanes)
+{
+  FR_DECLARE_STACK();
+  LightPolicy pol{sc, wb, reinterpret_cast<const float4*>(wb.light), f3(0.f), f3(0.f), f3(0.f), 0.f, 0.f, 0u};
+  trace_queue<ANY, false>(sc.bvh, pol, &wb.ctl->cursor[5], wb.ctl->n[Q_LIGHT], stack_column, kBlock, refill, tri_lanes);
 }
 
-// stand-alone batch query for the parity tests
+// stand-alone batch query for the parity tests: same driver and phases as the stages above
+struct BatchPolicy {
+  const SceneView& sc;
+  const uint32_t* submesh_offsets;
+  const float* rays;
+  float tmin0, tmax0;
+  uint32_t* out_id;
+  float* out_tuv;
+  unsigned long long* counters;
+  uint32_t i;
+  FR_D NoAnyHit anyhit() const { return NoAnyHit{}; }
+  FR_D void load(uint32_t item, float3& o, float3& d, float& tmin, float& tmax)
+  {
+    i = item;
+    o = f3(rays[6ull * i], rays[6ull * i + 1], rays[6ull * i + 2]);
+    d = f3(rays[6ull * i + 3], rays[6ull * i + 4], rays[6ull * i + 5]);
+    tmin = tmin0;
+    tmax = tmax0;
+  }
+  FR_D void retire(bool has, const HitRecord& h, const TraceCounters& cnt)
+  {
+    if (!has) return;
+    if (h.face != kNoHit) {
+      const uint32_t sm = sc.face_submesh[h.face];
+      out_id[2ull * i] = sm;
+      out_id[2ull * i + 1] = h.face - submesh_offsets[sm];
+      out_tuv[3ull * i] = h.t;
+      out_tuv[3ull * i + 1] = h.u;
+      out_tuv[3ull * i + 2] = h.v;
+    } else {
+      out_id[2ull * i] = out_id[2ull * i + 1] = kNoHit;
+      out_tuv[3ull * i] = out_tuv[3ull * i + 1] = out_tuv[3ull * i + 2] = 0.0f;
+    }
+    if (counters) {
+      atomicAdd(&counters[0], (unsigned long long)cnt.nodes);
+      atomicAdd(&counters[1], (unsigned long long)cnt.tris);
+    }
+  }
+};
+
 __global__ void __launch_bounds__(kBlock) k_trace_batch(SceneView sc, const uint32_t* __restrict__ submesh_offsets,
                                                         const float* __restrict__ rays, uint32_t n, float tmin,
                                                         float tmax, uint32_t* __restrict__ out_id,
-                                                        float* __restrict__ out_tuv, unsigned long long* counters)
+                                                        float* __restrict__ out_tuv, unsigned long long* counters,
+                                                        uint32_t* cursor, int refill, int tri_lanes)
 {
   FR_DECLARE_STACK();
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const float3 o = f3(rays[6ull * i], rays[6ull * i + 1], rays[6ull * i + 2]);
-  const float3 d = f3(rays[6ull * i + 3], rays[6ull * i + 4], rays[6ull * i + 5]);
-  TraceCounters cnt{0, 0};
-  const HitRecord h = traverse<false, true>(sc.bvh, o, d, tmin, tmax, st, NoAnyHit{}, &cnt);
-  if (h.face != kNoHit) {
-    const uint32_t sm = sc.face_submesh[h.face];
-    out_id[2ull * i] = sm;
-    out_id[2ull * i + 1] = h.face - submesh_offsets[sm];
-    out_tuv[3ull * i] = h.t;
-    out_tuv[3ull * i + 1] = h.u;
-    out_tuv[3ull * i + 2] = h.v;
-  } else {
-    out_id[2ull * i] = out_id[2ull * i + 1] = kNoHit;
-    out_tuv[3ull * i] = out_tuv[3ull * i + 1] = out_tuv[3ull * i + 2] = 0.0f;
-  }
-  if (counters) {
-    atomicAdd(&counters[0], (unsigned long long)cnt.nodes);
-    atomicAdd(&counters[1], (unsigned long long)cnt.tris);
-  }
+  BatchPolicy pol{sc, submesh_offsets, rays, tmin, tmax, out_id, out_tuv, counters, 0u};
+  trace_queue<false, true>(sc.bvh, pol, cursor, n, stack_column, kBlock, refill, tri_lanes);
 }
 
-int g_grid_closest = 0, g_grid_shadow = 0, g_grid_light = 0;
+int g_grid_closest = 0, g_grid_shadow = 0, g_grid_light = 0, g_grid_light_any = 0;
+
+// idle lanes per warp that trigger a refill (tunable for experiments: FRD_REFILL_LANES)
+int env_int(const char* name, int fallback)
+{
+  const char* e = getenv(name);
+  const int v = e ? (int)strtol(e, nullptr, 0) : fallback;
+  return v < 1 ? 1 : v;
+}
+int refill_lanes()
+{
+  static const int v = env_int("FRD_REFILL_LANES", 8);
+  return v;
+}
+// lanes with a pending triangle that trigger a triangle phase (closest-hit / any-hit kernels)
+int tri_lanes_closest()
+{
+  static const int v = env_int("FRD_TRI_LANES", 1);
+  return v;
+}
+int tri_lanes_any()
+{
+  static const int v = env_int("FRD_TRI_LANES_ANY", 1);
+  return v;
+}
 
 int persistent_grid(const void* kernel, int block)
 {
@@ -204,21 +294,27 @@ int persistent_grid(const void* kernel, int block)
 void launch_trace_closest(cudaStream_t s, const SceneView& sc, const WaveBuffers& wb, uint32_t depth)
 {
   if (!g_grid_closest) g_grid_closest = persistent_grid(reinterpret_cast<const void*>(k_trace_closest), kBlock);
-  k_trace_closest<<<g_grid_closest, kBlock, 0, s>>>(sc, wb, depth);
+  k_trace_closest<<<g_grid_closest, kBlock, 0, s>>>(sc, wb, depth, refill_lanes(), tri_lanes_closest());
   FR_CUDA_LAUNCH_CHECK();
 }
 
 void launch_trace_shadow(cudaStream_t s, const SceneView& sc, const WaveBuffers& wb, int which)
 {
   if (!g_grid_shadow) g_grid_shadow = persistent_grid(reinterpret_cast<const void*>(k_trace_shadow), kBlock);
-  k_trace_shadow<<<g_grid_shadow, kBlock, 0, s>>>(sc, wb, which);
+  k_trace_shadow<<<g_grid_shadow, kBlock, 0, s>>>(sc, wb, which, refill_lanes(), tri_lanes_any());
   FR_CUDA_LAUNCH_CHECK();
 }
 
 void launch_trace_light(cudaStream_t s, const SceneView& sc, const WaveBuffers& wb)
 {
-  if (!g_grid_light) g_grid_light = persistent_grid(reinterpret_cast<const void*>(k_trace_light), kBlock);
-  k_trace_light<<<g_grid_light, kBlock, 0, s>>>(sc, wb);
+  if (!g_grid_light) {
+    g_grid_light = persistent_grid(reinterpret_cast<const void*>(k_trace_light<false>), kBlock);
+    g_grid_light_any = persistent_grid(reinterpret_cast<const void*>(k_trace_light<true>), kBlock);
+  }
+  if (sc.n_lights == 0)
+    k_trace_light<true><<<g_grid_light_any, kBlock, 0, s>>>(sc, wb, refill_lanes(), tri_lanes_any());
+  else
+    k_trace_light<false><<<g_grid_light, kBlock, 0, s>>>(sc, wb, refill_lanes(), tri_lanes_closest());
   FR_CUDA_LAUNCH_CHECK();
 }
 
@@ -230,10 +326,14 @@ void trace_batch_closest(const SceneView& sc, const uint32_t* d_submesh_offsets,
   DevBuf<float> d_rays(6ull * n), d_tuv(3ull * n);
   DevBuf<uint32_t> d_id(2ull * n);
   DevBuf<unsigned long long> d_cnt(2);
+  DevBuf<uint32_t> d_cursor(1);
   d_cnt.zero();
+  d_cursor.zero();
   FR_CUDA_CHECK(cudaMemcpy(d_rays.get(), rays_host, sizeof(float) * 6ull * n, cudaMemcpyHostToDevice));
-  k_trace_batch<<<(n + kBlock - 1) / kBlock, kBlock>>>(sc, d_submesh_offsets, d_rays.get(), n, tmin, tmax, d_id.get(),
-                                                       d_tuv.get(), counters2_host ? d_cnt.get() : nullptr);
+  const int grid = std::min<int>((n + kBlock - 1) / kBlock, persistent_grid(reinterpret_cast<const void*>(k_trace_batch), kBlock));
+  k_trace_batch<<<grid, kBlock>>>(sc, d_submesh_offsets, d_rays.get(), n, tmin, tmax, d_id.get(), d_tuv.get(),
+                                  counters2_host ? d_cnt.get() : nullptr, d_cursor.get(), refill_lanes(),
+                                  tri_lanes_closest());
   FR_CUDA_LAUNCH_CHECK();
   FR_CUDA_CHECK(cudaMemcpy(out_id_host, d_id.get(), sizeof(uint32_t) * 2ull * n, cudaMemcpyDeviceToHost));
   FR_CUDA_CHECK(cudaMemcpy(out_tuv_host, d_tuv.get(), sizeof(float) * 3ull * n, cudaMemcpyDeviceToHost));
