@@ -14,7 +14,8 @@ import numpy as np
 from .types import MATERIAL_DTYPE, SceneArrays
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfredholm_b200.so")
+# FREDHOLM_B200_LIB: alternative build of the same library (kernel tuning experiments)
+LIB_PATH = os.environ.get("FREDHOLM_B200_LIB") or os.path.join(_HERE, "libfredholm_b200.so")
 
 
 class LibraryNotBuilt(RuntimeError):
@@ -66,6 +67,7 @@ SIGNATURES = {
     "fr_set_scene": (C.c_int, [_vp, _vp]),
     "fr_build_accel": (C.c_int, [_vp]),
     "fr_get_accel_info": (C.c_int, [_vp, _up, _fp, _u64p]),
+    "fr_get_accel_data": (C.c_int, [_vp, _vp, _vp]),
     "fr_set_time": (C.c_int, [_vp, C.c_float]),
     "fr_set_transforms": (C.c_int, [_vp, _fp, C.c_uint32]),
     "fr_set_directional_light": (C.c_int, [_vp, _fp, _fp, C.c_float]),
@@ -360,6 +362,18 @@ class Renderer:
         _check(lib().fr_get_accel_info(self._h, _u(out), C.byref(ms), C.byref(nbytes)))
         return dict(n_faces=int(out[0]), n_nodes=int(out[1]), depth=int(out[2]), build_ms=ms.value,
                     bytes=int(nbytes.value))
+
+    NODE_DTYPE = np.dtype([("p", "<f4", 3), ("e", "u1", 3), ("imask", "u1"), ("child_base", "<u4"),
+                           ("tri_base", "<u4"), ("meta", "u1", 8), ("qlo", "u1", (3, 8)), ("qhi", "u1", (3, 8))])
+
+    def accel_data(self):
+        """(nodes, tris): CWBVH nodes as NODE_DTYPE records (80 B) and leaf triangles (n,3,4) f32
+        (xyz + face id / flags bits in w)."""
+        info = self.accel_info()
+        nodes = np.zeros(info["n_nodes"], self.NODE_DTYPE)
+        tris = np.zeros((info["n_faces"], 3, 4), np.float32)
+        _check(lib().fr_get_accel_data(self._h, nodes.ctypes.data_as(_vp), tris.ctypes.data_as(_vp)))
+        return nodes, tris
 
     def set_time(self, t):
         _check(lib().fr_set_time(self._h, float(t)))

@@ -270,6 +270,16 @@ int fr_get_accel_info(fr_renderer* r, uint32_t* out3, float* build_ms, uint64_t*
   });
 }
 
+int fr_get_accel_data(fr_renderer* r, void* nodes80, void* tris48)
+{
+  return guarded([&] {
+    const frd::DeviceBvh& b = r->renderer.impl()->bvh;
+    FR_CUDA_CHECK(cudaDeviceSynchronize());
+    if (nodes80) FR_CUDA_CHECK(cudaMemcpy(nodes80, b.nodes.get(), sizeof(frd::Node8) * b.n_nodes, cudaMemcpyDeviceToHost));
+    if (tris48) FR_CUDA_CHECK(cudaMemcpy(tris48, b.tris.get(), 48ull * b.n_faces, cudaMemcpyDeviceToHost));
+  });
+}
+
 int fr_set_time(fr_renderer* r, float time)
 {
   return guarded([&] { r->renderer.set_time(time); });

@@ -27,6 +27,9 @@ namespace
 {
 
 constexpr int kBlock = 128;
+#ifndef FRD_SHADE_BLOCKS
+#define FRD_SHADE_BLOCKS 4
+#endif
 
 FR_D float pack_draws(const PathSampler& s) { return __uint_as_float(s.cmj_draws | (s.sobol_dim << 16)); }
 
@@ -158,7 +161,7 @@ __global__ void __launch_bounds__(kBlock) k_miss(SceneView sc, WaveBuffers wb)
 // strategies and the two BSDF samples run as (non-unrolled) loops so that the BSDF code
 // exists once per kernel, and queue appends happen with the whole warp converged.
 template <uint32_t MASK, bool TEX>
-__global__ void __launch_bounds__(kBlock) k_shade(WaveParams wp, SceneView sc, WaveBuffers wb, uint32_t depth, int cls)
+__global__ void __launch_bounds__(kBlock, FRD_SHADE_BLOCKS) k_shade(WaveParams wp, SceneView sc, WaveBuffers wb, uint32_t depth, int cls)
 {
   WaveControl* ctl = wb.ctl;
   const uint32_t n = ctl->n_class[cls];
@@ -338,6 +341,13 @@ __global__ void __launch_bounds__(kBlock) k_shade(WaveParams wp, SceneView sc, W
         if (s == 0) {
           w = throughput * f * cos_wi / pdf;
           want = nonzero3(w);
+          if (sc.n_lights == 0) {
+            // no emissive face anywhere: the MIS ray can only contribute by leaving the scene
+            // (__miss__light, pt.cu:531-543), so its contribution is known here and the ray
+            // becomes a plain visibility ray (cosine pdf of the sky NEE strategy)
+            const float mis = pdf / (pdf + cos_wi / kPi);
+            w = clamp3(w * mis, 0.0f, 1.0f) * sky_radiance(sc, dir);
+          }
         } else {
           throughput *= f * cos_wi / pdf;
           // raygen loop tail + head of the next iteration (pt.cu:455-471)
@@ -354,7 +364,7 @@ __global__ void __launch_bounds__(kBlock) k_shade(WaveParams wp, SceneView sc, W
         const uint32_t pos = queue_reserve(&ctl->n[Q_LIGHT], want);
         if (want) {
           float4* dst = reinterpret_cast<float4*>(wb.light + pos);
-          dst[0] = make_float4(o.x, o.y, o.z, pdf);
+          dst[0] = make_float4(o.x, o.y, o.z, sc.n_lights == 0 ? kRayMax : pdf);
           dst[1] = make_float4(dir.x, dir.y, dir.z, __uint_as_float(slot));
           dst[2] = make_float4(w.x, w.y, w.z, cos_wi);
         }

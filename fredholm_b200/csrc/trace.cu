@@ -123,7 +123,9 @@ struct ShadowPolicy {
 __global__ void __launch_bounds__(kBlock, 8) k_trace_shadow(SceneView sc, WaveBuffers wb, int which, int refill, int tri_lanes)
 {
   FR_DECLARE_STACK();
-  ShadowPolicy pol{sc, wb, reinterpret_cast<const float4*>(wb.shadow[which]), 0u, f3(0.f)};
+  // which == 3: the MIS-ray queue holding visibility records (scenes without emitters, shade.cu)
+  ShadowPolicy pol{sc, wb, reinterpret_cast<const float4*>(which < 3 ? wb.shadow[which] : (const ShadowRay*)wb.light), 0u,
+                   f3(0.f)};
   trace_queue<true, false>(sc.bvh, pol, &wb.ctl->cursor[2 + which], wb.ctl->n[Q_SHADOW0 + which], stack_column, kBlock,
                            refill, tri_lanes);
 }
@@ -192,15 +194,13 @@ struct LightPolicy {
   }
 };
 
-// ANY = true when the scene has no emissive face at all (n_lights == 0, the light list holds
-// every emissive face): then a MIS ray contributes only if it leaves the scene, so the first
-// accepted hit settles it and the closest one need not be found.
-template <bool ANY>
+// (scenes without any emissive face never get here: their MIS rays are visibility rays with
+// the sky contribution precomputed by the shade stage, traced by k_trace_shadow)
 __global__ void __launch_bounds__(kBlock, 8) k_trace_light(SceneView sc, WaveBuffers wb, int refill, int tri_lanes)
 {
   FR_DECLARE_STACK();
   LightPolicy pol{sc, wb, reinterpret_cast<const float4*>(wb.light), f3(0.f), f3(0.f), f3(0.f), 0.f, 0.f, 0u};
-  trace_queue<ANY, false>(sc.bvh, pol, &wb.ctl->cursor[5], wb.ctl->n[Q_LIGHT], stack_column, kBlock, refill, tri_lanes);
+  trace_queue<false, false>(sc.bvh, pol, &wb.ctl->cursor[5], wb.ctl->n[Q_LIGHT], stack_column, kBlock, refill, tri_lanes);
 }
 
 // stand-alone batch query for the parity tests: same driver and phases as the stages above
@@ -254,7 +254,7 @@ __global__ void __launch_bounds__(kBlock) k_trace_batch(SceneView sc, const uint
   trace_queue<false, true>(sc.bvh, pol, cursor, n, stack_column, kBlock, refill, tri_lanes);
 }
 
-int g_grid_closest = 0, g_grid_shadow = 0, g_grid_light = 0, g_grid_light_any = 0;
+int g_grid_closest = 0, g_grid_shadow = 0, g_grid_light = 0;
 
 // idle lanes per warp that trigger a refill (tunable for experiments: FRD_REFILL_LANES)
 int env_int(const char* name, int fallback)
@@ -307,14 +307,12 @@ void launch_trace_shadow(cudaStream_t s, const SceneView& sc, const WaveBuffers&
 
 void launch_trace_light(cudaStream_t s, const SceneView& sc, const WaveBuffers& wb)
 {
-  if (!g_grid_light) {
-    g_grid_light = persistent_grid(reinterpret_cast<const void*>(k_trace_light<false>), kBlock);
-    g_grid_light_any = persistent_grid(reinterpret_cast<const void*>(k_trace_light<true>), kBlock);
+  if (sc.n_lights == 0) {
+    launch_trace_shadow(s, sc, wb, 3);
+    return;
   }
-  if (sc.n_lights == 0)
-    k_trace_light<true><<<g_grid_light_any, kBlock, 0, s>>>(sc, wb, refill_lanes(), tri_lanes_any());
-  else
-    k_trace_light<false><<<g_grid_light, kBlock, 0, s>>>(sc, wb, refill_lanes(), tri_lanes_closest());
+  if (!g_grid_light) g_grid_light = persistent_grid(reinterpret_cast<const void*>(k_trace_light), kBlock);
+  k_trace_light<<<g_grid_light, kBlock, 0, s>>>(sc, wb, refill_lanes(), tri_lanes_closest());
   FR_CUDA_LAUNCH_CHECK();
 }
 

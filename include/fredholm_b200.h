@@ -76,6 +76,9 @@ int fr_get_texture_data(fr_renderer* r, uint32_t i, uint8_t* rgba8);
 int fr_build_accel(fr_renderer* r);
 /* out3 = n_faces, n_nodes, depth */
 int fr_get_accel_info(fr_renderer* r, uint32_t* out3, float* build_ms, uint64_t* bytes);
+/* structure inspection (tests / tools): copies the n_nodes 80-byte CWBVH nodes and the n_faces
+ * 48-byte leaf triangles (layout: fredholm_b200/csrc/bvh.cuh) to host memory; NULL skips */
+int fr_get_accel_data(fr_renderer* r, void* nodes80, void* tris48);
 /* Renderer::set_time (renderer.h:614-640) and direct transform replacement */
 int fr_set_time(fr_renderer* r, float time);
 int fr_set_transforms(fr_renderer* r, const float* transforms, uint32_t n_submeshes);
