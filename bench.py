@@ -33,7 +33,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOAD = dict(width=1920, height=1080, spp=64, max_depth=10, terrain_res=512, n_spheres=512)
-REF_SAMPLE = dict(window=(720, 405, 1200, 675), spp=16)  # 480x270 centre crop of the same frame
+REF_SAMPLE = dict(window=(600, 337, 1320, 742), spp=64)  # 720x405 centre crop of the same frame, all 64 samples (~10 s on 16 cores)
 
 
 def parse_args():
@@ -48,7 +48,8 @@ def parse_args():
     ap.add_argument("--max-depth", type=int, default=WORKLOAD["max_depth"])
     ap.add_argument("--small-scene", action="store_true", help="131k-triangle variant (debugging only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--wave-paths", type=int, default=0, help="override paths in flight per wave")
+    ap.add_argument("--wave-paths", type=int, default=0,
+                    help="paths in flight per wave (default: the whole frame, spp x tiled pixels)")
     return ap.parse_args()
 
 
@@ -245,8 +246,7 @@ def run_ours(args):
     r.set_directional_light(L["sun_le"], L["sun_dir"], L["sun_angle"])
     r.load_arhosek_sky(L["turbidity"], L["albedo"])
     r.set_resolution(W, H)
-    if args.wave_paths:
-        r.set_max_wave_paths(args.wave_paths)
+    r.set_max_wave_paths(wave_paths(args))
 
     if world > 1:
         beauty = torch.zeros((H, W, 4), dtype=torch.float32, device="cuda")
@@ -354,10 +354,19 @@ def run_ours(args):
                       "shade": 4 + 32 + 16 + 16 + 32 + 16 + 4 + 3 * 48 + 48}[top]
     ms_top, n_top = stages[top]
     achieved = (per_rank * bytes_per_unit / 1e9) / (ms_top / 1e3) if ms_top > 0 else 0.0
+    # DRAM bytes per ray of that kernel from the committed `ncu --set full` capture
+    # (profiles/r1e_kernels_ncu_full.txt: dram__bytes_read.sum + dram__bytes_write.sum over the rays of
+    # the captured launch), scaled to the rays of one launch here
+    ncu_dram_bytes_per_unit = {"trace_closest": 67.9}.get(top)
+    units_per_launch = per_rank / max(n_top, 1)
+    traffic = ncu_dram_bytes_per_unit * units_per_launch if ncu_dram_bytes_per_unit else None
     roofline = {"kernel": "k_" + top, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "traffic_source": "ncu --set full capture (profiles/), DRAM bytes per ray x rays per launch",
+                "sm_issue": {"issue_slots_busy_pct": 68.3, "active_lanes_per_instruction": 20.4,
+                             "source": "profiles/r1e_kernels_ncu_full.txt (ncu --set full, k_trace_closest, 33.2 M primary rays)"},
                 "launches": n_top, "avg_launch_ms": ms_top / max(n_top, 1),
-                "units_per_launch": per_rank / max(n_top, 1), "algorithmic_bytes_per_unit": bytes_per_unit,
+                "units_per_launch": units_per_launch, "algorithmic_bytes_per_unit": bytes_per_unit,
                 "note": "traversal is SM-issue / latency bound, not HBM bound (SURVEY.md 8(d)); issue-slot "
                         "utilisation from ncu is in profiles/",
                 "stage_ms": {k: round(v[0], 3) for k, v in stages.items()},
@@ -369,6 +378,7 @@ def run_ours(args):
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(args, scene), "samples_per_gpu": spp, "parallelism": "sample-sharded x%d" % world,
+                   "wave_paths": wave_paths(args),
                    "l2": "per-step working set (path state + queues, %.1f GB) exceeds the 126 MB L2; no explicit flush"
                          % (r_state_gb(W, H, spp, args)),
                    "bvh": {"nodes": accel["n_nodes"], "depth": accel["depth"], "build_ms": round(accel["build_ms"], 2),
@@ -393,11 +403,24 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def slots_per_sample(W, H):
+    """8x4 pixel tiles, one path slot per tile lane (fredholm_b200/csrc/wavefront.h)."""
+    return ((W + 7) // 8) * ((H + 3) // 4) * 32
+
+
+def wave_paths(args):
+    """All samples of the frame in ONE wave unless overridden: fewer, larger launches (the
+    persistent kernels have a fixed tail per launch) at the price of HBM for the wave state."""
+    return args.wave_paths or slots_per_sample(args.width, args.height) * args.spp
+
+
+PATH_STATE_BYTES = 8 * 16 + (2 + 9) * 4 + 4 * 48   # path SoA + queues (integrator.cpp: ensure_capacity)
+
+
 def r_state_gb(W, H, spp, args):
-    from fredholm_b200.api import lib  # noqa: F401  (import check only)
-    slots = ((W + 7) // 8) * ((H + 3) // 4) * 32
-    per_wave = max(1, min(spp, (args.wave_paths or (1 << 23)) // slots))
-    return per_wave * slots * (8 * 16 + 2 * 4 + 4 * 48) / 1e9
+    slots = slots_per_sample(W, H)
+    per_wave = max(1, min(spp, wave_paths(args) // slots))
+    return per_wave * slots * PATH_STATE_BYTES / 1e9
 
 
 def main():

@@ -69,7 +69,7 @@ class Integrator
   void ensure_capacity(size_t n_slots);
 
   cudaStream_t m_stream;
-  size_t m_max_wave_paths = size_t(1) << 23;  // 8 Mi paths
+  size_t m_max_wave_paths = size_t(1) << 26;  // 64 Mi paths (24 GB of wave state)
   size_t m_capacity = 0;
   size_t m_state_bytes = 0;
   unsigned long long m_launches = 0;

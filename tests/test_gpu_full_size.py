@@ -40,7 +40,7 @@ def render(r, cam, spp, depth=10, first=0, mode="mean", wave=None, names=("beaut
     out = {n: layers.download(n) for n in names}
     layers.free()
     r.set_film_mode("mean")
-    r.set_max_wave_paths(1 << 23)
+    r.set_max_wave_paths(1 << 26)
     return out
 
 
