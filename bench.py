@@ -184,7 +184,7 @@ def run_reference(args):
         "cpu_baseline": {"value": value, "unit": "Mpaths/s", "cores": cores, "kind": "reference", "sample": sample},
         "e2e": {"value": value, "unit": "Mpaths/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------
@@ -249,6 +249,9 @@ def run_ours(args):
     r.set_max_wave_paths(wave_paths(args))
 
     if world > 1:
+        # torch's current stream := the renderer's stream, so the NCCL reduce is stream-ordered
+        # after the render kernels and the CUDA events recorded on that stream bracket both
+        torch.cuda.set_stream(torch.cuda.ExternalStream(r.stream(), device=torch.device("cuda", local_rank)))
         beauty = torch.zeros((H, W, 4), dtype=torch.float32, device="cuda")
         layers = {"beauty": beauty.data_ptr()}
         r.set_film_mode("sum")
@@ -268,7 +271,6 @@ def run_ours(args):
         r.set_sample_offset(rank * spp)
         r.render(cam, (0, 0, 0), layers, spp, depth)
         if world > 1:
-            r.wait()
             dist.reduce(beauty, dst=0, op=dist.ReduceOp.SUM)
             if rank == 0:
                 r.scale_layers(layers, 1.0 / (spp * world))
@@ -298,15 +300,12 @@ def run_ours(args):
         clear()
         sync_all()
         e0 = r.record_event()
-        t0 = time.perf_counter()
         step()
         e1 = r.record_event()
         sync_all()
-        wall_ms = 1e3 * (time.perf_counter() - t0)
-        ev_ms = api.event_elapsed_ms(e0, e1)
-        # single GPU: device time from CUDA events on the launching stream; multi GPU: the
-        # region spans two streams (render + NCCL), so the synchronised wall clock is used
-        step_ms.append(ev_ms if world == 1 else wall_ms)
+        # device time from CUDA events on the launching stream (render kernels and, for N > 1,
+        # the NCCL reduce, which torch orders on the same stream); max over ranks below
+        step_ms.append(api.event_elapsed_ms(e0, e1))
     stats = r.statistics()
     stages = r.stage_times()
     r.set_stage_timing(False)
@@ -398,9 +397,18 @@ def run_ours(args):
         line["cpu_baseline"] = cpu_baseline(args, scene)
     else:
         line["cpu_baseline"] = None
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+_REAL_STDOUT = None
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def slots_per_sample(W, H):
@@ -425,6 +433,12 @@ def r_state_gb(W, H, spp, args):
 
 def main():
     args = parse_args()
+    # the contract is ONE JSON line on stdout: native libraries (NCCL's version banner) write to
+    # fd 1 directly, so fd 1 is pointed at stderr while working and only the line goes to the real stdout
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:

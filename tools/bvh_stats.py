@@ -38,3 +38,15 @@ for k in range(3):
 print("triangles outside their leaf box:", bad)
 faces = tris[:, 0, 3].view(np.uint32)
 print("every face exactly once:", np.array_equal(np.sort(faces), np.arange(len(faces), dtype=np.uint32)))
+# depth of every node / leaf (children of node i start at child_base, inner children in slot order)
+depth = np.zeros(len(nodes), dtype=np.int32)
+order = np.argsort(nodes["child_base"], kind="stable")  # parents precede children in the array (level order)
+for i in range(len(nodes)):
+    k = int(inner[i].sum())
+    if k:
+        b = int(nodes["child_base"][i])
+        depth[b:b + k] = depth[i] + 1
+leaf_depth = np.repeat(depth, leaf.sum(1))
+w = np.repeat(cnt.sum(1), 1)
+print("node depth hist", np.bincount(depth))
+print("mean leaf depth (per triangle) %.2f  max %d" % ((depth * cnt.sum(1)).sum() / cnt.sum(), depth.max()))
