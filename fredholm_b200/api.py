@@ -109,6 +109,11 @@ SIGNATURES = {
     "fr_device_synchronize": (C.c_int, []),
     "fr_host_alloc_pinned": (_vp, [C.c_size_t]),
     "fr_host_free_pinned": (C.c_int, [_vp]),
+    "fr_image8_load": (C.c_int, [C.c_char_p, _up, _up]),
+    "fr_image8_copy": (C.c_int, [_u8p]),
+    "fr_imagef_load": (C.c_int, [C.c_char_p, _up, _up]),
+    "fr_imagef_copy": (C.c_int, [_fp]),
+    "fr_write_png": (C.c_int, [C.c_char_p, _u8p, C.c_uint32, C.c_uint32, C.c_uint32]),
     "fr_trace_closest": (C.c_int, [_vp, _fp, C.c_uint32, C.c_float, C.c_float, _up, _fp, _u64p]),
     "fr_primary_rays": (C.c_int, [_vp, _fp, C.c_float, C.c_float, C.c_float, C.c_uint32, _fp]),
     "fr_sampler_sequence": (C.c_int, [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_char_p, _fp]),
@@ -274,6 +279,31 @@ def _read_scene(handle, sizes_fn, arrays_fn, texinfo_fn, texdata_fn) -> SceneArr
     s.has_camera = bool(sz[5])
     s.camera_transform = cam
     return s
+
+
+def load_image8(path):
+    """(H, W, 4) uint8 as fredholm::Texture holds it: row 0 = bottom row of the file."""
+    w, h = C.c_uint32(), C.c_uint32()
+    _check(lib().fr_image8_load(os.fsencode(str(path)), C.byref(w), C.byref(h)))
+    img = np.zeros((h.value, w.value, 4), np.uint8)
+    _check(lib().fr_image8_copy(img.ctypes.data_as(_u8p)))
+    return img
+
+
+def load_imagef(path):
+    """(H, W, 4) float32 as fredholm::FloatTexture holds it: row 0 = top row of the file."""
+    w, h = C.c_uint32(), C.c_uint32()
+    _check(lib().fr_imagef_load(os.fsencode(str(path)), C.byref(w), C.byref(h)))
+    img = np.zeros((h.value, w.value, 4), np.float32)
+    _check(lib().fr_imagef_copy(img.ctypes.data_as(_fp)))
+    return img
+
+
+def write_png(path, pixels):
+    """pixels: (H, W, 3|4) uint8, row 0 = top row."""
+    a = np.ascontiguousarray(pixels, dtype=np.uint8)
+    assert a.ndim == 3 and a.shape[2] in (3, 4)
+    _check(lib().fr_write_png(os.fsencode(str(path)), a.ctypes.data_as(_u8p), a.shape[1], a.shape[0], a.shape[2]))
 
 
 class Scene:

@@ -1,5 +1,6 @@
 // extern "C" facade over fredholm::Renderer (see include/fredholm_b200.h).
 #include "fredholm_b200.h"
+#include "image_codec.h"
 
 #include <cstring>
 #include <string>
@@ -528,6 +529,41 @@ int fr_host_free_pinned(void* p)
 int fr_device_synchronize(void)
 {
   return guarded([&] { FR_CUDA_CHECK(cudaDeviceSynchronize()); });
+}
+
+namespace
+{
+thread_local fredholm::Texture t_image8;
+thread_local fredholm::FloatTexture t_imagef;
+}  // namespace
+
+int fr_image8_load(const char* path, uint32_t* width, uint32_t* height)
+{
+  return guarded([&] {
+    t_image8 = fredholm::Texture(std::filesystem::path(path), fredholm::TextureType::NONCOLOR);
+    *width = t_image8.m_width;
+    *height = t_image8.m_height;
+  });
+}
+int fr_image8_copy(uint8_t* rgba8)
+{
+  return guarded([&] { std::memcpy(rgba8, t_image8.m_data.data(), 4 * t_image8.m_data.size()); });
+}
+int fr_imagef_load(const char* path, uint32_t* width, uint32_t* height)
+{
+  return guarded([&] {
+    t_imagef = fredholm::FloatTexture(std::filesystem::path(path));
+    *width = t_imagef.m_width;
+    *height = t_imagef.m_height;
+  });
+}
+int fr_imagef_copy(float* rgba32f)
+{
+  return guarded([&] { std::memcpy(rgba32f, t_imagef.m_data.data(), 16 * t_imagef.m_data.size()); });
+}
+int fr_write_png(const char* path, const uint8_t* pixels, uint32_t width, uint32_t height, uint32_t channels)
+{
+  return guarded([&] { fredholm::codec::write_png(path, pixels, (int)width, (int)height, (int)channels); });
 }
 
 int fr_trace_closest(fr_renderer* r, const float* rays, uint32_t n, float tmin, float tmax, uint32_t* out_id,

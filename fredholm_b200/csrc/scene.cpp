@@ -697,6 +697,4 @@ void Scene::load_obj(const std::filesystem::path& filepath)
   }
 }
 
-void Scene::update_transform() {}
-
 }  // namespace fredholm

@@ -289,3 +289,117 @@ def write_obj(scene: SceneArrays, directory, name="scene", with_attributes=True)
                     lines.append("f %d %d %d\n" % (a, b, c))
             f.write("".join(lines))
     return obj_path
+
+
+def write_gltf(scene: SceneArrays, directory, name="scene", embed=False, node_transforms=None, parents=None,
+               animations=None, image_files=None, clearcoat=False):
+    """Serialises `scene` as name.gltf (+ name.bin unless embed=True, which uses a base64 data URI).
+
+    One mesh + one node per sub-mesh (16-bit indices, so every sub-mesh may reference at most
+    65536 distinct vertices); node i gets node_transforms[i] = {"translation": .., "rotation":
+    (x, y, z, w), "scale": ..} or {"matrix": 16 column-major floats}; parents[i] = parent node of
+    node i (roots otherwise); animations = [{"node": i, "translation": (times, values), "rotation":
+    (times, xyzw), "scale": (times, values)}]; image_files = file names (relative to `directory`)
+    of the images behind texture ids 0..n-1 (the caller writes the files).  Returns the path."""
+    import base64
+    import json
+    os.makedirs(directory, exist_ok=True)
+    blob = bytearray()
+    views, accessors = [], []
+
+    def add(data, comp, typ, minmax=False):
+        while len(blob) % 4:
+            blob.append(0)
+        a = np.ascontiguousarray(data)
+        views.append({"buffer": 0, "byteOffset": len(blob), "byteLength": a.nbytes})
+        blob.extend(a.tobytes())
+        acc = {"bufferView": len(views) - 1, "componentType": comp, "count": int(a.shape[0]), "type": typ}
+        if minmax:
+            acc["min"] = [float(v) for v in np.atleast_1d(a.min(axis=0))]
+            acc["max"] = [float(v) for v in np.atleast_1d(a.max(axis=0))]
+        accessors.append(acc)
+        return len(accessors) - 1
+
+    meshes, nodes = [], []
+    n_sub = len(scene.submesh_offsets)
+    for s in range(n_sub):
+        off, cnt = int(scene.submesh_offsets[s]), int(scene.submesh_n_faces[s])
+        prims = []
+        faces = np.arange(off, off + cnt)
+        mids = scene.material_ids[faces]
+        for mid in np.unique(mids):          # one primitive per material
+            f = faces[mids == mid]
+            idx = scene.indices[f].reshape(-1)
+            used, local = np.unique(idx, return_inverse=True)
+            assert len(used) <= 65536, "sub-mesh too large for 16-bit indices"
+            uv = scene.texcoords[used].astype(np.float32).copy()
+            uv[:, 1] = 1.0 - uv[:, 1]        # the loader stores (u, 1 - v)
+            prims.append({"attributes": {"POSITION": add(scene.vertices[used].astype(np.float32), 5126, "VEC3", True),
+                                         "NORMAL": add(scene.normals[used].astype(np.float32), 5126, "VEC3"),
+                                         "TEXCOORD_0": add(uv, 5126, "VEC2")},
+                          "indices": add(local.astype(np.uint16), 5123, "SCALAR"), "material": int(mid)})
+        meshes.append({"primitives": prims})
+        node = {"mesh": s, "name": "node%d" % s}
+        if node_transforms and s < len(node_transforms) and node_transforms[s]:
+            for k, v in node_transforms[s].items():
+                node[k] = [float(x) for x in v]
+        nodes.append(node)
+    roots = list(range(n_sub))
+    if parents:
+        for child, parent in parents.items():
+            nodes[parent].setdefault("children", []).append(int(child))
+            roots.remove(child)
+
+    def tex(i):
+        return {"index": int(i)}
+
+    materials = []
+    for m in scene.materials:
+        pbr = {"baseColorFactor": [float(v) for v in m["base_color"]] + [1.0],
+               "roughnessFactor": float(m["specular_roughness"]), "metallicFactor": float(m["metalness"])}
+        if m["base_color_texture_id"] >= 0:
+            pbr["baseColorTexture"] = tex(m["base_color_texture_id"])
+        if m["metallic_roughness_texture_id"] >= 0:
+            pbr["metallicRoughnessTexture"] = tex(m["metallic_roughness_texture_id"])
+        jm = {"pbrMetallicRoughness": pbr, "emissiveFactor": [float(v) for v in m["emission_color"]]}
+        if m["emission_texture_id"] >= 0:
+            jm["emissiveTexture"] = tex(m["emission_texture_id"])
+        if m["normalmap_texture_id"] >= 0:
+            jm["normalTexture"] = tex(m["normalmap_texture_id"])
+        if clearcoat:
+            jm["extensions"] = {"KHR_materials_clearcoat": {"clearcoatFactor": float(m["coat"]),
+                                                            "clearcoatRoughnessFactor": float(m["coat_roughness"])}}
+        materials.append(jm)
+
+    janims = []
+    for a in animations or []:
+        samplers, channels = [], []
+        for path, typ in (("translation", "VEC3"), ("rotation", "VEC4"), ("scale", "VEC3")):
+            if path in a:
+                times, values = a[path]
+                samplers.append({"input": add(np.asarray(times, np.float32), 5126, "SCALAR", True),
+                                 "output": add(np.asarray(values, np.float32), 5126, typ), "interpolation": "LINEAR"})
+                channels.append({"sampler": len(samplers) - 1, "target": {"node": int(a["node"]), "path": path}})
+        janims.append({"samplers": samplers, "channels": channels})
+
+    doc = {"asset": {"version": "2.0", "generator": "fredholm_b200.scenes.write_gltf"}, "scene": 0,
+           "scenes": [{"nodes": roots}], "nodes": nodes, "meshes": meshes, "materials": materials,
+           "accessors": accessors, "bufferViews": views}
+    if clearcoat:
+        doc["extensionsUsed"] = ["KHR_materials_clearcoat"]
+    if janims:
+        doc["animations"] = janims
+    if image_files:
+        doc["images"] = [{"uri": f} for f in image_files]
+        doc["textures"] = [{"source": i} for i in range(len(image_files))]
+    if embed:
+        doc["buffers"] = [{"byteLength": len(blob),
+                           "uri": "data:application/octet-stream;base64," + base64.b64encode(bytes(blob)).decode()}]
+    else:
+        with open(os.path.join(directory, name + ".bin"), "wb") as f:
+            f.write(bytes(blob))
+        doc["buffers"] = [{"byteLength": len(blob), "uri": name + ".bin"}]
+    path = os.path.join(directory, name + ".gltf")
+    with open(path, "w") as f:
+        json.dump(doc, f, indent=1)
+    return path

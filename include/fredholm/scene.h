@@ -59,7 +59,8 @@ struct quat {
 };
 
 struct Animation {
-  int node_idx = -1;  // target node (index in the source file)
+  int node_idx = -1;   // target node (index in the source file)
+  int root_slot = -1;  // position of that node in Scene::m_nodes (only root nodes can be driven)
 
   std::vector<float> translation_input;
   std::vector<vec3> translation_output;

@@ -162,6 +162,20 @@ int fr_device_synchronize(void);
 void* fr_host_alloc_pinned(size_t bytes);
 int fr_host_free_pinned(void* p);
 
+/* ---- image files on the boundary (host only, no device needed) ----
+ * fr_image8_load  = what fredholm::Texture(path, type) holds (fredholm/src/scene.cpp:7-37: stbi_load,
+ *                   4 channels, vertical flip -> row 0 is the BOTTOM row): PNG and JPEG
+ * fr_imagef_load  = what fredholm::FloatTexture(path) holds (scene.cpp:39-67: stbi_loadf, no flip):
+ *                   Radiance .hdr, or an 8-bit file through the gamma-2.2 rule
+ * The decoded image stays in a per-thread slot until the matching *_copy call.
+ * fr_write_png    = stbi_write_png(path, w, h, channels, data, w * channels) of the frame savers
+ *                   (app/controller.cpp:291-308, app/rtcamp8.cpp:286-293); channels 3 or 4 */
+int fr_image8_load(const char* path, uint32_t* width, uint32_t* height);
+int fr_image8_copy(uint8_t* rgba8);
+int fr_imagef_load(const char* path, uint32_t* width, uint32_t* height);
+int fr_imagef_copy(float* rgba32f);
+int fr_write_png(const char* path, const uint8_t* pixels, uint32_t width, uint32_t height, uint32_t channels);
+
 /* ---- stage-level entry points used by the parity tests ---- */
 /* closest hit for n rays (6 floats each: origin, direction): out_id = (instance, primitive)
  * or 0xffffffff, out_tuv = (t, u, v); counters2 (optional) = nodes visited, triangles tested */

@@ -228,6 +228,28 @@ class Oracle:
         return out
 
 
+def load_image8(path):
+    """fredholm::Texture(path) of the reference (stb_image, flipped): (H, W, 4) uint8."""
+    L = lib()
+    w, h = C.c_uint32(), C.c_uint32()
+    if L.orc_image8_load(os.fsencode(str(path)), C.byref(w), C.byref(h)) != 0:
+        raise RuntimeError(L.orc_last_error().decode())
+    img = np.zeros((h.value, w.value, 4), np.uint8)
+    L.orc_image8_copy(img.ctypes.data_as(_vp))
+    return img
+
+
+def load_imagef(path):
+    """fredholm::FloatTexture(path) of the reference (stbi_loadf, not flipped): (H, W, 4) float32."""
+    L = lib()
+    w, h = C.c_uint32(), C.c_uint32()
+    if L.orc_imagef_load(os.fsencode(str(path)), C.byref(w), C.byref(h)) != 0:
+        raise RuntimeError(L.orc_last_error().decode())
+    img = np.zeros((h.value, w.value, 4), np.float32)
+    L.orc_imagef_copy(_f(img))
+    return img
+
+
 def sampler_sequence(width, height, seed, image_idx, n_spp, kinds):
     n_out = sum(1 if k == "1" else 2 for k in kinds)
     out = np.zeros(n_out, np.float32)

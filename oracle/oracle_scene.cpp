@@ -124,6 +124,39 @@ void orc_scene_texture_copy(uint i, unsigned char* rgba8)
   std::memcpy(rgba8, t.m_data.data(), 4 * (size_t)t.m_width * t.m_height);
 }
 
+// The reference's image decoding on its own (Texture / FloatTexture constructors,
+// scene.cpp:7-67 -> stb_image): 8-bit RGBA, bottom row first; float RGBA, top row first.
+static std::vector<uchar4> g_tex;
+static std::vector<float4> g_ftex;
+int orc_image8_load(const char* path, uint* w, uint* h)
+{
+  try {
+    const fredholm::Texture t(path, fredholm::TextureType::NONCOLOR);
+    g_tex = t.m_data;
+    *w = t.m_width;
+    *h = t.m_height;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return -1;
+  }
+  return 0;
+}
+void orc_image8_copy(unsigned char* rgba8) { std::memcpy(rgba8, g_tex.data(), 4 * g_tex.size()); }
+int orc_imagef_load(const char* path, uint* w, uint* h)
+{
+  try {
+    const fredholm::FloatTexture t(path);
+    g_ftex = t.m_data;
+    *w = t.m_width;
+    *h = t.m_height;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return -1;
+  }
+  return 0;
+}
+void orc_imagef_copy(float* rgba32f) { std::memcpy(rgba32f, g_ftex.data(), 16 * g_ftex.size()); }
+
 // Camera (camera.h:51-69): camera-to-world 3x4 (row-major, as Renderer::render
 // packs it, renderer.h:678-684) for a camera at `origin` looking down -z.
 void orc_camera_transform(const float* origin, float* out12)
