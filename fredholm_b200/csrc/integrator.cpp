@@ -1,9 +1,49 @@
 #include "integrator.h"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace frd
 {
+
+namespace
+{
+uint32_t env_u32(const char* name, uint32_t fallback)
+{
+  const char* e = getenv(name);
+  return e ? (uint32_t)strtoul(e, nullptr, 0) : fallback;
+}
+}  // namespace
+
+Integrator::Integrator(cudaStream_t stream) : m_stream(stream)
+{
+  m_sort_mask = env_u32("FRD_SORT", 0u);
+  m_sort_bits = std::min(std::max(env_u32("FRD_SORT_BITS", 4u), 1u), 7u);
+}
+
+void Integrator::set_coherence_sort(uint32_t queue_mask, uint32_t cell_bits)
+{
+  m_sort_mask = queue_mask;
+  m_sort_bits = std::min(std::max(cell_bits, 1u), 7u);
+}
+
+// sorts queue `which` and returns the order to trace it in (nullptr: sort disabled for it)
+const uint32_t* Integrator::sorted(const SceneView& scene, const WaveBuffers& wb, int which, bool use_octant)
+{
+  SortGrid g;
+  g.lo = scene.bounds_lo;
+  const float cells = (float)(1u << m_sort_bits);
+  const float ex = std::max(scene.bounds_hi.x - scene.bounds_lo.x, 1e-20f);
+  const float ey = std::max(scene.bounds_hi.y - scene.bounds_lo.y, 1e-20f);
+  const float ez = std::max(scene.bounds_hi.z - scene.bounds_lo.z, 1e-20f);
+  g.inv_cell = make_float3(cells / ex, cells / ey, cells / ez);
+  g.cell_bits = m_sort_bits;
+  g.use_octant = use_octant ? 1u : 0u;
+  m_sort_bins.reserve(size_t(1) << (3 * m_sort_bits + 3));
+  launch_coherence_sort(m_stream, wb, g, which, m_sort_keys.get(), m_sort_bins.get(), m_sort_out.get());
+  m_launches += 2;  // three kernels, one of them counted by stage()
+  return m_sort_out.get();
+}
 
 Integrator::~Integrator()
 {
@@ -79,9 +119,11 @@ void Integrator::ensure_capacity(size_t n_slots)
   for (auto& s : m_shadow) s.alloc(n_slots);
   for (auto& q : m_class_queue) q.alloc(n_slots);
   m_light.alloc(n_slots);
+  m_sort_keys.alloc(n_slots);
+  m_sort_out.alloc(n_slots);
   m_capacity = n_slots;
   m_state_bytes = n_slots * (8 * sizeof(float4) + (2 + CLS_COUNT) * sizeof(uint32_t) + 3 * sizeof(ShadowRay) +
-                             sizeof(LightRay));
+                             sizeof(LightRay) + 2 * sizeof(uint32_t));
 }
 
 void Integrator::render(const SceneView& scene, const fredholm::CameraParams& camera, uint32_t width,
@@ -122,14 +164,30 @@ void Integrator::render(const SceneView& scene, const fredholm::CameraParams& ca
     stage(STAGE_ADVANCE, [&] { launch_wave_begin(m_stream, wb, (unsigned long long)wp.n_samples * width * height); });
     stage(STAGE_GENERATE, [&] { launch_generate(m_stream, wp, wb); });
     for (uint32_t depth = 0; depth < max_depth; ++depth) {
-      stage(STAGE_TRACE_CLOSEST, [&] { launch_trace_closest(m_stream, scene, wb, depth); });
+      // coherence sort (queue management, booked under "advance"): each queue is sorted right
+      // before it is traced, so one scratch order buffer serves all of them
+      const uint32_t* order = nullptr;
+      auto sort_queue = [&](uint32_t bit, int which, bool use_octant) {
+        order = nullptr;
+        if (m_sort_mask & bit) stage(STAGE_ADVANCE, [&] { order = sorted(scene, wb, which, use_octant); });
+      };
+      if (depth > 0) sort_queue(1u, SORT_RADIANCE0 + (int)(depth & 1u), true);
+      stage(STAGE_TRACE_CLOSEST, [&] { launch_trace_closest(m_stream, scene, wb, depth, order); });
       if (depth == 0) stage(STAGE_SHADE, [&] { launch_miss(m_stream, scene, wb); });
       for (int c = 0; c < CLS_MISS; ++c)
         if (class_mask & (1u << c)) stage(STAGE_SHADE, [&] { launch_shade(m_stream, wp, scene, wb, depth, c); });
-      if (scene.has_dir_light) stage(STAGE_TRACE_SHADOW, [&] { launch_trace_shadow(m_stream, scene, wb, 0); });
-      stage(STAGE_TRACE_SHADOW, [&] { launch_trace_shadow(m_stream, scene, wb, 1); });
-      if (scene.n_lights > 0) stage(STAGE_TRACE_SHADOW, [&] { launch_trace_shadow(m_stream, scene, wb, 2); });
-      stage(STAGE_TRACE_LIGHT, [&] { launch_trace_light(m_stream, scene, wb); });
+      if (scene.has_dir_light) {
+        sort_queue(2u, SORT_SHADOW0, false);  // all sun rays point the same way
+        stage(STAGE_TRACE_SHADOW, [&] { launch_trace_shadow(m_stream, scene, wb, 0, order); });
+      }
+      sort_queue(4u, SORT_SHADOW1, true);
+      stage(STAGE_TRACE_SHADOW, [&] { launch_trace_shadow(m_stream, scene, wb, 1, order); });
+      if (scene.n_lights > 0) {
+        sort_queue(8u, SORT_SHADOW2, true);
+        stage(STAGE_TRACE_SHADOW, [&] { launch_trace_shadow(m_stream, scene, wb, 2, order); });
+      }
+      sort_queue(16u, SORT_LIGHT, true);
+      stage(STAGE_TRACE_LIGHT, [&] { launch_trace_light(m_stream, scene, wb, order); });
       stage(STAGE_ADVANCE, [&] { launch_advance(m_stream, wb); });
     }
     stage(STAGE_FILM, [&] { launch_film(m_stream, wp, wb, layers, film_mode); });

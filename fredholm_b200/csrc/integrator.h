@@ -39,7 +39,7 @@ struct StageTimes {
 class Integrator
 {
  public:
-  explicit Integrator(cudaStream_t stream) : m_stream(stream) {}
+  explicit Integrator(cudaStream_t stream);
 
   // paths kept in flight per wave; rounded down to whole samples (at least one)
   void set_max_wave_paths(size_t n) { m_max_wave_paths = n; }
@@ -59,6 +59,12 @@ class Integrator
   void reset_stats();
 
   size_t state_bytes() const { return m_state_bytes; }
+
+  // Coherence sort (sort.cu).  queue_mask: bit 0 radiance rays (bounces >= 1), bit 1 sun NEE rays,
+  // bit 2 sky NEE rays, bit 3 area-light NEE rays, bit 4 MIS rays.  cell_bits: 2^bits origin
+  // cells per axis.  Defaults come from FRD_SORT / FRD_SORT_BITS.
+  void set_coherence_sort(uint32_t queue_mask, uint32_t cell_bits);
+  uint32_t coherence_sort_mask() const { return m_sort_mask; }
 
   // per-stage device time (CUDA events around every launch, on the launching stream)
   void set_stage_timing(bool on) { m_time_stages = on; }
@@ -91,6 +97,10 @@ class Integrator
   DevBuf<ShadowRay> m_shadow[3];
   DevBuf<LightRay> m_light;
   DevBuf<WaveControl> m_ctl;
+
+  uint32_t m_sort_mask, m_sort_bits;
+  DevBuf<uint32_t> m_sort_keys, m_sort_out, m_sort_bins;
+  const uint32_t* sorted(const SceneView& scene, const WaveBuffers& wb, int which, bool use_octant);
 };
 
 }  // namespace frd

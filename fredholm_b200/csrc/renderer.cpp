@@ -270,6 +270,8 @@ frd::SceneView Renderer::Impl::view(const float3& bg_color) const
   v.lights = d_lights.get();
   v.n_lights = n_lights;
   v.bvh = bvh.view();
+  v.bounds_lo = make_float3(bvh.bounds_lo[0], bvh.bounds_lo[1], bvh.bounds_lo[2]);
+  v.bounds_hi = make_float3(bvh.bounds_hi[0], bvh.bounds_hi[1], bvh.bounds_hi[2]);
   v.has_dir_light = has_dir_light ? 1 : 0;
   v.dir_light = dir_light;
   if (has_dir_light) {

@@ -82,10 +82,11 @@ struct ClosestPolicy {
   }
 };
 
-__global__ void __launch_bounds__(kBlock, 8) k_trace_closest(SceneView sc, WaveBuffers wb, uint32_t depth, int refill, int tri_lanes)
+__global__ void __launch_bounds__(kBlock, 8) k_trace_closest(SceneView sc, WaveBuffers wb, uint32_t depth, int refill, int tri_lanes,
+                                                             const uint32_t* order)
 {
   FR_DECLARE_STACK();
-  ClosestPolicy pol{sc, wb, wb.queue[depth & 1u], depth, 0u};
+  ClosestPolicy pol{sc, wb, order ? order : wb.queue[depth & 1u], depth, 0u};
   trace_queue<false, false>(sc.bvh, pol, &wb.ctl->cursor[0], wb.ctl->n[Q_CUR], stack_column, kBlock, refill, tri_lanes);
 }
 
@@ -94,11 +95,13 @@ struct ShadowPolicy {
   const SceneView& sc;
   const WaveBuffers& wb;
   const float4* q;
+  const uint32_t* order;
   uint32_t path;
   float3 c;
   FR_D AlphaTest anyhit() const { return AlphaTest{&sc}; }
   FR_D void load(uint32_t item, float3& o, float3& d, float& tmin, float& tmax)
   {
+    if (order) item = order[item];
     const float4 r0 = q[3ull * item], r1 = q[3ull * item + 1], r2 = q[3ull * item + 2];
     o = f3(r0);
     d = f3(r1);
@@ -120,12 +123,13 @@ struct ShadowPolicy {
   }
 };
 
-__global__ void __launch_bounds__(kBlock, 8) k_trace_shadow(SceneView sc, WaveBuffers wb, int which, int refill, int tri_lanes)
+__global__ void __launch_bounds__(kBlock, 8) k_trace_shadow(SceneView sc, WaveBuffers wb, int which, int refill, int tri_lanes,
+                                                            const uint32_t* order)
 {
   FR_DECLARE_STACK();
   // which == 3: the MIS-ray queue holding visibility records (scenes without emitters, shade.cu)
-  ShadowPolicy pol{sc, wb, reinterpret_cast<const float4*>(which < 3 ? wb.shadow[which] : (const ShadowRay*)wb.light), 0u,
-                   f3(0.f)};
+  ShadowPolicy pol{sc, wb, reinterpret_cast<const float4*>(which < 3 ? wb.shadow[which] : (const ShadowRay*)wb.light), order,
+                   0u, f3(0.f)};
   trace_queue<true, false>(sc.bvh, pol, &wb.ctl->cursor[2 + which], wb.ctl->n[Q_SHADOW0 + which], stack_column, kBlock,
                            refill, tri_lanes);
 }
@@ -135,12 +139,14 @@ struct LightPolicy {
   const SceneView& sc;
   const WaveBuffers& wb;
   const float4* q;
+  const uint32_t* order;
   float3 o, d, w;
   float pdf_bsdf, cos_wi;
   uint32_t path;
   FR_D AlphaTest anyhit() const { return AlphaTest{&sc}; }
   FR_D void load(uint32_t item, float3& ro, float3& rd, float& tmin, float& tmax)
   {
+    if (order) item = order[item];
     const float4 r0 = q[3ull * item], r1 = q[3ull * item + 1], r2 = q[3ull * item + 2];
     ro = o = f3(r0);
     rd = d = f3(r1);
@@ -196,10 +202,11 @@ struct LightPolicy {
 
 // (scenes without any emissive face never get here: their MIS rays are visibility rays with
 // the sky contribution precomputed by the shade stage, traced by k_trace_shadow)
-__global__ void __launch_bounds__(kBlock, 8) k_trace_light(SceneView sc, WaveBuffers wb, int refill, int tri_lanes)
+__global__ void __launch_bounds__(kBlock, 8) k_trace_light(SceneView sc, WaveBuffers wb, int refill, int tri_lanes,
+                                                           const uint32_t* order)
 {
   FR_DECLARE_STACK();
-  LightPolicy pol{sc, wb, reinterpret_cast<const float4*>(wb.light), f3(0.f), f3(0.f), f3(0.f), 0.f, 0.f, 0u};
+  LightPolicy pol{sc, wb, reinterpret_cast<const float4*>(wb.light), order, f3(0.f), f3(0.f), f3(0.f), 0.f, 0.f, 0u};
   trace_queue<false, false>(sc.bvh, pol, &wb.ctl->cursor[5], wb.ctl->n[Q_LIGHT], stack_column, kBlock, refill, tri_lanes);
 }
 
@@ -291,28 +298,29 @@ int persistent_grid(const void* kernel, int block)
 
 }  // namespace
 
-void launch_trace_closest(cudaStream_t s, const SceneView& sc, const WaveBuffers& wb, uint32_t depth)
+void launch_trace_closest(cudaStream_t s, const SceneView& sc, const WaveBuffers& wb, uint32_t depth,
+                          const uint32_t* order)
 {
   if (!g_grid_closest) g_grid_closest = persistent_grid(reinterpret_cast<const void*>(k_trace_closest), kBlock);
-  k_trace_closest<<<g_grid_closest, kBlock, 0, s>>>(sc, wb, depth, refill_lanes(), tri_lanes_closest());
+  k_trace_closest<<<g_grid_closest, kBlock, 0, s>>>(sc, wb, depth, refill_lanes(), tri_lanes_closest(), order);
   FR_CUDA_LAUNCH_CHECK();
 }
 
-void launch_trace_shadow(cudaStream_t s, const SceneView& sc, const WaveBuffers& wb, int which)
+void launch_trace_shadow(cudaStream_t s, const SceneView& sc, const WaveBuffers& wb, int which, const uint32_t* order)
 {
   if (!g_grid_shadow) g_grid_shadow = persistent_grid(reinterpret_cast<const void*>(k_trace_shadow), kBlock);
-  k_trace_shadow<<<g_grid_shadow, kBlock, 0, s>>>(sc, wb, which, refill_lanes(), tri_lanes_any());
+  k_trace_shadow<<<g_grid_shadow, kBlock, 0, s>>>(sc, wb, which, refill_lanes(), tri_lanes_any(), order);
   FR_CUDA_LAUNCH_CHECK();
 }
 
-void launch_trace_light(cudaStream_t s, const SceneView& sc, const WaveBuffers& wb)
+void launch_trace_light(cudaStream_t s, const SceneView& sc, const WaveBuffers& wb, const uint32_t* order)
 {
   if (sc.n_lights == 0) {
-    launch_trace_shadow(s, sc, wb, 3);
+    launch_trace_shadow(s, sc, wb, 3, order);
     return;
   }
   if (!g_grid_light) g_grid_light = persistent_grid(reinterpret_cast<const void*>(k_trace_light), kBlock);
-  k_trace_light<<<g_grid_light, kBlock, 0, s>>>(sc, wb, refill_lanes(), tri_lanes_closest());
+  k_trace_light<<<g_grid_light, kBlock, 0, s>>>(sc, wb, refill_lanes(), tri_lanes_closest(), order);
   FR_CUDA_LAUNCH_CHECK();
 }
 

@@ -38,6 +38,7 @@ struct SceneView {
   const fredholm::AreaLight* lights;
   uint32_t n_lights;
   BvhView bvh;
+  float3 bounds_lo, bounds_hi;  // world bounds of the geometry (coherence-sort grid)
 
   // lights & sky
   int has_dir_light;
@@ -149,6 +150,16 @@ __host__ __device__ inline uint32_t pixel_to_slot(const FilmGeom& g, uint32_t x,
 {
   return ((y >> 2) * g.tiles_x + (x >> 3)) * 32u + ((y & 3u) << 3) + (x & 7u);
 }
+
+// Coherence sort (sort.cu): which queue, and the grid the ray origins are binned on.
+enum SortQueue : int { SORT_RADIANCE0 = 0, SORT_RADIANCE1, SORT_SHADOW0, SORT_SHADOW1, SORT_SHADOW2, SORT_LIGHT };
+struct SortGrid {
+  float3 lo;          // scene bounds, lower corner
+  float3 inv_cell;    // cells per world unit, per axis
+  uint32_t cell_bits;  // 2^cell_bits cells per axis (<= 10)
+  uint32_t use_octant;  // append the direction octant to the key
+};
+__host__ __device__ inline uint32_t sort_bins(const SortGrid& g) { return 1u << (3u * g.cell_bits + (g.use_octant ? 3u : 0u)); }
 
 struct WaveParams {
   FilmGeom film;

@@ -24,9 +24,18 @@ void launch_film(cudaStream_t s, const WaveParams& wp, const WaveBuffers& wb, co
 void launch_scale_layers(cudaStream_t s, const fredholm::RenderLayer& layers, uint32_t n_pixels, float scale);
 
 // trace.cu
-void launch_trace_closest(cudaStream_t s, const SceneView& sc, const WaveBuffers& wb, uint32_t depth);
-void launch_trace_shadow(cudaStream_t s, const SceneView& sc, const WaveBuffers& wb, int which);
-void launch_trace_light(cudaStream_t s, const SceneView& sc, const WaveBuffers& wb);
+// `order` (optional, device): the order in which the queue items are traced (coherence sort);
+// for the radiance queue it holds path slots, for the record queues item indices
+void launch_trace_closest(cudaStream_t s, const SceneView& sc, const WaveBuffers& wb, uint32_t depth,
+                          const uint32_t* order = nullptr);
+void launch_trace_shadow(cudaStream_t s, const SceneView& sc, const WaveBuffers& wb, int which,
+                         const uint32_t* order = nullptr);
+void launch_trace_light(cudaStream_t s, const SceneView& sc, const WaveBuffers& wb, const uint32_t* order = nullptr);
+
+// sort.cu: counting sort of queue `which` (SortQueue) by origin cell + direction octant.
+// keys: [queue size] scratch, bins: [sort_bins(g)] scratch, out: [queue size] sorted order
+void launch_coherence_sort(cudaStream_t s, const WaveBuffers& wb, const SortGrid& g, int which, uint32_t* keys,
+                           uint32_t* bins, uint32_t* out);
 // stand-alone batch query (tests, tools): rays are (o.xyz, d.xyz) per entry;
 // out_id = (instance, primitive) or 0xffffffff, out_tuv = (t, u, v).  All HOST pointers.
 // counters (optional, host): nodes visited, triangles tested
