@@ -15,7 +15,10 @@ namespace frd
 namespace
 {
 
-constexpr int kLeafMax = 3;  // triangles per leaf slot (unary count fits 3 bits)
+#ifndef FR_LEAF_MAX
+#define FR_LEAF_MAX 3
+#endif
+constexpr int kLeafMax = FR_LEAF_MAX;  // triangles per leaf slot (unary count fits 3 bits)
 
 // ---- stage 1: world-space triangles + scene bounds --------------------------------
 __device__ __forceinline__ float xf_row(const float4& r, const float3& p)
@@ -268,6 +271,28 @@ __global__ void k_collapse(uint32_t level_begin, uint32_t level_end, uint32_t* _
       c[best] = ch2.x;
       c[nc++] = ch2.y;
     }
+#ifndef FR_NO_LEAF_SPLIT
+    // slots left over: split multi-triangle leaves (largest first) so that their triangles get
+    // boxes of their own -- no extra node, fewer triangle tests
+    while (nc < 8) {
+      int best = -1;
+      float best_area = -1.0f;
+      for (int k = 0; k < nc; ++k) {
+        const uint32_t cnt = tri_count(t, n, c[k]);
+        if (cnt > 1u && cnt <= (uint32_t)kLeafMax) {
+          const float a = half_area(t.lo[c[k]], t.hi[c[k]]);
+          if (a > best_area) {
+            best_area = a;
+            best = k;
+          }
+        }
+      }
+      if (best < 0) break;
+      const uint2 ch2 = t.child[c[best]];
+      c[best] = ch2.x;
+      c[nc++] = ch2.y;
+    }
+#endif
   }
 
   const float4 nlo = t.lo[b2], nhi = t.hi[b2];
