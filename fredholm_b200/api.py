@@ -35,6 +35,23 @@ class _PostProcessParams(C.Structure):
                 ("ISO", C.c_float), ("chromatic_aberration", C.c_float)]
 
 
+class _BatchConfig(C.Structure):
+    _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("n_spp", C.c_uint32), ("max_depth", C.c_uint32),
+                ("post", _PostProcessParams), ("denoise", C.c_int), ("upscale", C.c_int),
+                ("dn_iterations", C.c_int), ("dn_sigma_color", C.c_float), ("dn_sigma_albedo", C.c_float),
+                ("dn_albedo_floor", C.c_float), ("dn_firefly_k", C.c_float), ("fps", C.c_float), ("start_time", C.c_float),
+                ("max_time", C.c_float), ("kill_time_s", C.c_float), ("first_frame", C.c_uint32),
+                ("frame_stride", C.c_uint32), ("max_frames", C.c_uint32), ("bg_color", C.c_float * 3),
+                ("animate", C.c_int), ("output_dir", C.c_char_p), ("n_save_threads", C.c_uint32),
+                ("n_slots", C.c_uint32)]
+
+
+class _FrameRecord(C.Structure):
+    _fields_ = [("frame_idx", C.c_uint32)] + [(n, C.c_float) for n in (
+        "time", "accel_ms", "render_ms", "denoise_ms", "post_ms", "transfer_ms", "encode_ms", "save_ms")] + [
+        ("png_bytes", C.c_uint64)]
+
+
 _fp = C.POINTER(C.c_float)
 _up = C.POINTER(C.c_uint32)
 _u8p = C.POINTER(C.c_uint8)
@@ -101,6 +118,10 @@ SIGNATURES = {
     "fr_get_stream": (C.c_uint64, [_vp]),
     "fr_post_process": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.POINTER(_PostProcessParams), _vp]),
     "fr_tone_mapping": (C.c_int, [_vp, C.c_int, C.c_int, C.c_float, C.c_float, _vp]),
+    "fr_denoise": (C.c_int, [_vp, _vp, _vp, _vp, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_float, C.c_float,
+                             C.c_float, C.c_float]),
+    "fr_batch_run": (C.c_int, [_vp, C.POINTER(_BatchConfig), _fp, C.c_uint32, C.c_float, C.c_float, C.c_float,
+                               C.POINTER(_FrameRecord), C.c_uint32, _u8p, _up, C.POINTER(C.c_double)]),
     "fr_device_alloc": (_vp, [C.c_size_t]),
     "fr_device_free": (C.c_int, [_vp]),
     "fr_device_memset": (C.c_int, [_vp, C.c_int, C.c_size_t]),
@@ -487,6 +508,47 @@ class Renderer:
                                           int(max_depth)))
         return res
 
+    def batch_run(self, camera, width, height, n_spp, max_depth, n_frames, camera_path=None, output_dir=None,
+                  keep_frames=True, denoise=True, upscale=False, use_bloom=True, bloom_threshold=2.0,
+                  bloom_sigma=5.0, ISO=80.0, chromatic_aberration=1.0, fps=24.0, start_time=0.0, max_time=9.5,
+                  kill_time_s=590.0, first_frame=0, frame_stride=1, bg_color=(0, 0, 0), animate=True,
+                  n_save_threads=2, n_slots=3, dn_iterations=0, dn_sigma_color=0.0, dn_sigma_albedo=0.0,
+                  dn_albedo_floor=0.0, dn_firefly_k=-1.0):
+        """fredholm::FrameBatch::run (app/rtcamp8.cpp render + save loop).  Returns
+        (records: list of dict, frames: (n, H, W, 4) uint8 or None, info dict)."""
+        cfg = _BatchConfig()
+        cfg.width, cfg.height, cfg.n_spp, cfg.max_depth = int(width), int(height), int(n_spp), int(max_depth)
+        cfg.post = _PostProcessParams(1 if use_bloom else 0, bloom_threshold, bloom_sigma, ISO, chromatic_aberration)
+        cfg.denoise, cfg.upscale = (1 if denoise else 0), (1 if upscale else 0)
+        cfg.dn_iterations, cfg.dn_sigma_color = int(dn_iterations), float(dn_sigma_color)
+        cfg.dn_sigma_albedo, cfg.dn_albedo_floor = float(dn_sigma_albedo), float(dn_albedo_floor)
+        cfg.dn_firefly_k = float(dn_firefly_k)
+        cfg.fps, cfg.start_time, cfg.max_time, cfg.kill_time_s = fps, start_time, max_time, kill_time_s
+        cfg.first_frame, cfg.frame_stride, cfg.max_frames = int(first_frame), int(frame_stride), int(n_frames)
+        cfg.bg_color = (C.c_float * 3)(*[float(v) for v in bg_color])
+        cfg.animate = 1 if animate else 0
+        cfg.output_dir = str(output_dir).encode() if output_dir else None
+        cfg.n_save_threads, cfg.n_slots = int(n_save_threads), int(n_slots)
+        if camera_path is not None:
+            path = np.ascontiguousarray(camera_path, dtype=np.float32).reshape(-1, 12)
+            n_path = len(path)
+        else:
+            path = _f32(camera.transform, 12).reshape(1, 12)
+            n_path = 0
+        ow, oh = (2 * width, 2 * height) if upscale else (width, height)
+        recs = (_FrameRecord * int(n_frames))()
+        frames = np.zeros((int(n_frames), oh, ow, 4), np.uint8) if keep_frames else None
+        out5 = np.zeros(5, np.uint32)
+        wall = C.c_double(0.0)
+        _check(lib().fr_batch_run(self._h, C.byref(cfg), _f(path), n_path, camera.fov, camera.F, camera.focus, recs,
+                                  int(n_frames), frames.ctypes.data_as(_u8p) if keep_frames else None, _u(out5),
+                                  C.byref(wall)))
+        n = int(out5[0])
+        records = [{name: getattr(recs[i], name) for name, _ in _FrameRecord._fields_} for i in range(n)]
+        info = dict(n_frames=n, out_width=int(out5[1]), out_height=int(out5[2]), killed=bool(out5[3]),
+                    wall_s=wall.value)
+        return records, (frames[:n] if keep_frames else None), info
+
     def scale_layers(self, layers, scale):
         st = layers.struct() if isinstance(layers, DeviceLayers) else None
         if st is None:
@@ -581,6 +643,14 @@ def post_process(beauty_in, high, temp, width, height, out, use_bloom=True, bloo
                  ISO=80.0, chromatic_aberration=1.0):
     p = _PostProcessParams(1 if use_bloom else 0, bloom_threshold, bloom_sigma, ISO, chromatic_aberration)
     _check(lib().fr_post_process(beauty_in, high, temp, width, height, C.byref(p), out))
+
+
+def denoise(beauty, normal, albedo, out, width, height, upscale=False, iterations=0, sigma_color=0.0,
+            sigma_albedo=0.0, albedo_floor=0.0, firefly_k=-1.0):
+    """fredholm::Denoiser one-shot on device pointers (defaults when a parameter is 0; firefly_k < 0)."""
+    _check(lib().fr_denoise(beauty, normal, albedo, out, int(width), int(height), 1 if upscale else 0,
+                            int(iterations), float(sigma_color), float(sigma_albedo), float(albedo_floor),
+                            float(firefly_k)))
 
 
 def tone_mapping(beauty_in, width, height, out, ISO=80.0, chromatic_aberration=1.0):

@@ -2,10 +2,13 @@
 #include "fredholm_b200.h"
 #include "image_codec.h"
 
+#include <algorithm>
 #include <cstring>
 #include <string>
 #include <vector>
 
+#include "fredholm/batch.h"
+#include "fredholm/denoiser.h"
 #include "kernels/post-process.h"
 #include "renderer_impl.h"
 
@@ -491,6 +494,102 @@ int fr_tone_mapping(const void* beauty_in_dev, int width, int height, float ISO,
     tone_mapping_kernel_launch(static_cast<const float4*>(beauty_in_dev), width, height, ISO, chromatic_aberration,
                                static_cast<float4*>(beauty_out_dev));
     FR_CUDA_CHECK(cudaDeviceSynchronize());
+  });
+}
+
+int fr_denoise(const void* beauty_dev, const void* normal_dev, const void* albedo_dev, void* denoised_dev,
+               uint32_t width, uint32_t height, int upscale, int iterations, float sigma_color, float sigma_albedo,
+               float albedo_floor, float firefly_k)
+{
+  return guarded([&] {
+    Denoiser d(width, height, static_cast<const float4*>(beauty_dev), static_cast<const float4*>(normal_dev),
+               static_cast<const float4*>(albedo_dev), static_cast<float4*>(denoised_dev), upscale != 0);
+    DenoiserParams p;
+    if (iterations > 0) p.iterations = iterations;
+    if (sigma_color > 0.0f) p.sigma_color = sigma_color;
+    if (sigma_albedo > 0.0f) p.sigma_albedo = sigma_albedo;
+    if (albedo_floor > 0.0f) p.albedo_floor = albedo_floor;
+    if (firefly_k >= 0.0f) p.firefly_k = firefly_k;
+    d.set_params(p);
+    d.denoise();
+    d.wait_for_completion();
+  });
+}
+
+int fr_batch_run(fr_renderer* r, const fr_batch_config* c, const float* camera_transforms12, uint32_t n_camera_frames,
+                 float fov, float F, float focus, fr_frame_record* records, uint32_t max_records,
+                 uint8_t* frames_rgba8, uint32_t* out5, double* wall_s)
+{
+  return guarded([&] {
+    BatchConfig cfg;
+    cfg.width = c->width;
+    cfg.height = c->height;
+    cfg.n_spp = c->n_spp;
+    cfg.max_depth = c->max_depth;
+    cfg.post.use_bloom = c->post.use_bloom != 0;
+    cfg.post.bloom_threshold = c->post.bloom_threshold;
+    cfg.post.bloom_sigma = c->post.bloom_sigma;
+    cfg.post.ISO = c->post.ISO;
+    cfg.post.chromatic_aberration = c->post.chromatic_aberration;
+    cfg.denoise = c->denoise != 0;
+    cfg.upscale = c->upscale != 0;
+    if (c->dn_iterations > 0) cfg.denoiser.iterations = c->dn_iterations;
+    if (c->dn_sigma_color > 0.0f) cfg.denoiser.sigma_color = c->dn_sigma_color;
+    if (c->dn_sigma_albedo > 0.0f) cfg.denoiser.sigma_albedo = c->dn_sigma_albedo;
+    if (c->dn_albedo_floor > 0.0f) cfg.denoiser.albedo_floor = c->dn_albedo_floor;
+    if (c->dn_firefly_k >= 0.0f) cfg.denoiser.firefly_k = c->dn_firefly_k;
+    cfg.fps = c->fps;
+    cfg.start_time = c->start_time;
+    cfg.max_time = c->max_time;
+    cfg.kill_time_s = c->kill_time_s;
+    cfg.first_frame = c->first_frame;
+    cfg.frame_stride = c->frame_stride;
+    cfg.max_frames = std::min(c->max_frames, max_records);
+    for (int i = 0; i < 3; ++i) cfg.bg_color[i] = c->bg_color[i];
+    cfg.animate = c->animate != 0;
+    cfg.output_dir = c->output_dir ? c->output_dir : "";
+    cfg.n_save_threads = c->n_save_threads;
+    cfg.n_slots = c->n_slots;
+    cfg.keep_frames = frames_rgba8 != nullptr;
+
+    auto set_camera = [&](Camera& cam, uint32_t i) {
+      const float* t = camera_transforms12 + 12ull * i;
+      cam.m_transform = mat4();
+      for (int row = 0; row < 3; ++row)
+        for (int col = 0; col < 4; ++col) cam.m_transform[col][row] = t[4 * row + col];
+    };
+    Camera camera;
+    camera.m_fov = fov;
+    camera.m_F = F;
+    camera.m_focus = focus;
+    set_camera(camera, 0);
+    FrameBatch batch(r->renderer, cfg);
+    FrameBatch::FrameHook hook;
+    if (n_camera_frames > 0)
+      hook = [&](uint32_t frame_idx, float, Camera& cam) { set_camera(cam, std::min(frame_idx, n_camera_frames - 1)); };
+    const BatchResult res = batch.run(camera, hook);
+    const size_t frame_bytes = (size_t)res.out_width * res.out_height * 4;
+    for (size_t i = 0; i < res.frames.size(); ++i) {
+      const FrameRecord& f = res.frames[i];
+      fr_frame_record& o = records[i];
+      o.frame_idx = f.frame_idx;
+      o.time = f.time;
+      o.accel_ms = f.accel_ms;
+      o.render_ms = f.render_ms;
+      o.denoise_ms = f.denoise_ms;
+      o.post_ms = f.post_ms;
+      o.transfer_ms = f.transfer_ms;
+      o.encode_ms = f.encode_ms;
+      o.save_ms = f.save_ms;
+      o.png_bytes = f.png_bytes;
+      if (frames_rgba8) std::memcpy(frames_rgba8 + i * frame_bytes, f.rgba8.data(), frame_bytes);
+    }
+    out5[0] = (uint32_t)res.frames.size();
+    out5[1] = res.out_width;
+    out5[2] = res.out_height;
+    out5[3] = res.killed ? 1u : 0u;
+    out5[4] = 0u;
+    if (wall_s) *wall_s = res.wall_s;
   });
 }
 

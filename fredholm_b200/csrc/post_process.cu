@@ -200,40 +200,74 @@ frd::DevBuf<float4>& scratch(size_t n)
   return buf;
 }
 
-void launch_tone_map(const float4* in, int width, int height, float ISO, float ca, float4* out)
+void launch_tone_map(const float4* in, int width, int height, float ISO, float ca, float4* out, cudaStream_t s)
 {
   const dim3 block(32, 8);
   const dim3 grid((width + 31) / 32, (height + 7) / 8);
-  k_tone_map<<<grid, block>>>(in, width, height, exposure_from_iso(ISO), ca, out);
+  k_tone_map<<<grid, block, 0, s>>>(in, width, height, exposure_from_iso(ISO), ca, out);
   FR_CUDA_LAUNCH_CHECK();
+}
+
+// float4 -> RGBA8 exactly as the reference's applications convert on the host
+// (app/rtcamp8.cpp:268-280, app/controller.cpp:291-305): (uchar)clamp(255 * v, 0, 255), alpha 255
+__global__ void __launch_bounds__(256) k_quantize_rgba8(const float4* __restrict__ in, size_t n,
+                                                        uchar4* __restrict__ out)
+{
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 v = in[i];
+  uchar4 o;
+  o.x = (unsigned char)fminf(fmaxf(__fmul_rn(255.0f, v.x), 0.0f), 255.0f);
+  o.y = (unsigned char)fminf(fmaxf(__fmul_rn(255.0f, v.y), 0.0f), 255.0f);
+  o.z = (unsigned char)fminf(fmaxf(__fmul_rn(255.0f, v.z), 0.0f), 255.0f);
+  o.w = 255;
+  out[i] = o;
 }
 
 }  // namespace
 
-void post_process_kernel_launch(const float4* beauty_in, float4* beauty_high_luminance, float4* beauty_temp,
-                                int width, int height, const PostProcessParams& params, float4* beauty_out)
+namespace frd
+{
+
+void post_process_async(const float4* beauty_in, float4* beauty_high_luminance, float4* beauty_temp, int width,
+                        int height, const PostProcessParams& params, float4* beauty_out, cudaStream_t s)
 {
   if (params.use_bloom) {
     frd::DevBuf<float4>& tmp = scratch((size_t)width * height);
     const dim3 grid_h((width + kRowSeg - 1) / kRowSeg, height);
-    k_bloom_h<<<grid_h, kRowSeg>>>(beauty_in, beauty_high_luminance, width, height, params.bloom_threshold,
-                                   params.bloom_sigma, tmp.get());
+    k_bloom_h<<<grid_h, kRowSeg, 0, s>>>(beauty_in, beauty_high_luminance, width, height, params.bloom_threshold,
+                                         params.bloom_sigma, tmp.get());
     FR_CUDA_LAUNCH_CHECK();
     const dim3 block_v(kTile, 8);
     const dim3 grid_v((width + kTile - 1) / kTile, (height + kTile - 1) / kTile);
-    k_bloom_v<<<grid_v, block_v>>>(beauty_in, tmp.get(), width, height, params.bloom_sigma, beauty_temp);
+    k_bloom_v<<<grid_v, block_v, 0, s>>>(beauty_in, tmp.get(), width, height, params.bloom_sigma, beauty_temp);
     FR_CUDA_LAUNCH_CHECK();
   } else {
     const dim3 block(32, 8);
     const dim3 grid((width + 31) / 32, (height + 7) / 8);
-    k_copy<<<grid, block>>>(beauty_in, width, height, beauty_temp);
+    k_copy<<<grid, block, 0, s>>>(beauty_in, width, height, beauty_temp);
     FR_CUDA_LAUNCH_CHECK();
   }
-  launch_tone_map(beauty_temp, width, height, params.ISO, params.chromatic_aberration, beauty_out);
+  launch_tone_map(beauty_temp, width, height, params.ISO, params.chromatic_aberration, beauty_out, s);
+}
+
+void quantize_rgba8_async(const float4* in, size_t n_pixels, uchar4* out, cudaStream_t s)
+{
+  if (n_pixels == 0) return;
+  k_quantize_rgba8<<<(unsigned)((n_pixels + 255) / 256), 256, 0, s>>>(in, n_pixels, out);
+  FR_CUDA_LAUNCH_CHECK();
+}
+
+}  // namespace frd
+
+void post_process_kernel_launch(const float4* beauty_in, float4* beauty_high_luminance, float4* beauty_temp,
+                                int width, int height, const PostProcessParams& params, float4* beauty_out)
+{
+  frd::post_process_async(beauty_in, beauty_high_luminance, beauty_temp, width, height, params, beauty_out, 0);
 }
 
 void tone_mapping_kernel_launch(const float4* beauty_in, int width, int height, float ISO,
                                 float chromatic_aberration, float4* beauty_out)
 {
-  launch_tone_map(beauty_in, width, height, ISO, chromatic_aberration, beauty_out);
+  launch_tone_map(beauty_in, width, height, ISO, chromatic_aberration, beauty_out, 0);
 }

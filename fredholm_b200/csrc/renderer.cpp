@@ -355,7 +355,15 @@ void Renderer::build_ias()
 void Renderer::set_time(float time)
 {
   FR_CUDA_CHECK(cudaSetDevice(m_impl->device));
+  // the reference re-uploads every transform and rebuilds its IAS on each call
+  // (renderer.h:614-640); here the world-space tree only depends on the sub-mesh
+  // transforms, so a time step that moves nothing but the camera keeps the tree
+  const std::vector<mat4> before = m_impl->scene.m_transforms;
   m_impl->scene.update_animation(time);
+  const std::vector<mat4>& after = m_impl->scene.m_transforms;
+  const bool moved = before.size() != after.size() ||
+                     (!after.empty() && std::memcmp(before.data(), after.data(), sizeof(mat4) * after.size()) != 0);
+  if (!moved && m_impl->accel_valid) return;
   m_impl->upload_transforms();
   m_impl->build_accel();
 }

@@ -11,6 +11,10 @@ file loaders on both sides.
   standard_surface_scene() BASELINE.json config 2/3: terrain + spheres, 1 048 576
                            triangles by default, 8 Standard-Surface materials
                            (metal / coat / rough glass / sheen / diffuse)
+  instanced_scene()        BASELINE.json config 4: 52 M triangles, terrain + 3072 transformed
+                           placements of a 16 K-triangle mesh, all diffuse
+  textured_scene()         BASELINE.json config 5: config 2's scene with procedural base-colour
+                           / roughness / normal-map textures
 """
 import os
 
@@ -231,6 +235,130 @@ def standard_surface_scene(terrain_res=512, n_spheres=512, sphere_res=(32, 16), 
                        material_ids=np.concatenate(mats),
                        materials=np.array(standard_surface_materials(), dtype=MATERIAL_DTYPE),
                        submesh_offsets=np.array(offsets, np.uint32), submesh_n_faces=np.array(counts, np.uint32))
+
+
+def procedural_textures(res=1024, seed=0xC5):
+    """Hash-noise RGBA8 textures for BASELINE.json config 5: [0] base colour (COLOR: sRGB decoded
+    on fetch), [1] specular roughness (NONCOLOR, .x), [2] tangent-space normal map (NONCOLOR).
+    Multi-octave value noise so that bilinear fetches see structure at every scale."""
+    yy, xx = np.meshgrid(np.arange(res), np.arange(res), indexing="ij")
+
+    def octave(cells, salt):
+        cx, cy = xx.astype(np.float64) / res * cells, yy.astype(np.float64) / res * cells
+        ix, iy = np.floor(cx).astype(np.int64), np.floor(cy).astype(np.int64)
+        fx, fy = cx - ix, cy - iy
+        fx, fy = fx * fx * (3 - 2 * fx), fy * fy * (3 - 2 * fy)
+
+        def lat(a, b):   # periodic lattice: wrap addressing stays seamless
+            return _hash01(((a % cells) * 73856093 ^ (b % cells) * 19349663 ^ (seed * 977 + salt)) & 0xFFFFFFFF
+                           ).astype(np.float64)
+        return (lat(ix, iy) * (1 - fx) + lat(ix + 1, iy) * fx) * (1 - fy) + \
+               (lat(ix, iy + 1) * (1 - fx) + lat(ix + 1, iy + 1) * fx) * fy
+
+    def fbm(salt):
+        return (octave(8, salt) + 0.5 * octave(16, salt + 1) + 0.25 * octave(64, salt + 2) +
+                0.125 * octave(256, salt + 3)) / 1.875
+
+    def rgba(r, g, b, a=1.0):
+        img = np.stack([r, g, b, np.broadcast_to(a, r.shape)], -1)
+        return np.ascontiguousarray(np.clip(np.round(img * 255.0), 0, 255).astype(np.uint8))
+
+    n0, n1, n2 = fbm(1), fbm(11), fbm(21)
+    checker = (((xx * 16 // res) + (yy * 16 // res)) & 1).astype(np.float64)
+    base = rgba(0.25 + 0.6 * n0 * (0.6 + 0.4 * checker), 0.2 + 0.6 * n1, 0.15 + 0.5 * n2 * (1.0 - 0.5 * checker))
+    rough = rgba(0.08 + 0.6 * n1, 0.08 + 0.6 * n1, 0.08 + 0.6 * n1)
+    hgt = fbm(31)
+    dx = np.roll(hgt, -1, axis=1) - np.roll(hgt, 1, axis=1)
+    dy = np.roll(hgt, -1, axis=0) - np.roll(hgt, 1, axis=0)
+    nrm = np.stack([-dx * res / 64.0, -dy * res / 64.0, np.ones_like(dx)], -1)
+    nrm /= np.linalg.norm(nrm, axis=-1, keepdims=True)
+    normal = rgba(0.5 + 0.5 * nrm[..., 0], 0.5 + 0.5 * nrm[..., 1], 0.5 + 0.5 * nrm[..., 2])
+    return [(base, True), (rough, False), (normal, False)]
+
+
+def textured_scene(tex_res=1024, **kw):
+    """BASELINE.json config 5 content: the Standard-Surface scene with procedurally generated
+    textures on the terrain (base colour + roughness + normal map), the car paint (base
+    colour) and the plastic (roughness + normal map): exercises CLS_GENERIC_TEX shading."""
+    s = standard_surface_scene(**kw)
+    s.textures = procedural_textures(tex_res)
+    m = s.materials
+    m[0]["base_color_texture_id"], m[0]["specular_roughness_texture_id"], m[0]["normalmap_texture_id"] = 0, 1, 2
+    m[3]["base_color_texture_id"] = 0
+    m[7]["specular_roughness_texture_id"], m[7]["normalmap_texture_id"] = 1, 2
+    return s
+
+
+def instanced_scene(n_instances=3072, mesh_res=(128, 64), terrain_res=1024, seed=0x50C4):
+    """BASELINE.json config 4: a unique terrain (2 * terrain_res^2 triangles) plus n_instances
+    placements of one UV-sphere-like blob mesh (2 * mesh_res[0] * mesh_res[1] triangles each),
+    all diffuse.  Defaults: 2 097 152 + 3072 * 16 384 = 52 428 800 triangles.  Like the
+    reference's glTF path (scene.cpp:730-822) every placement is its own
+    sub-mesh with its own copy of the mesh and its own transform (instance i = sub-mesh i)."""
+    R = terrain_res
+    ext = 400.0
+    gx, gz = np.meshgrid(np.arange(R + 1), np.arange(R + 1), indexing="xy")
+    x = (gx.astype(np.float32) / R - 0.5) * ext
+    z = (gz.astype(np.float32) / R - 0.5) * ext
+    y = (6.0 * np.sin(x * 0.031) * np.cos(z * 0.027) + 2.0 * np.sin(x * 0.11 + 1.3) * np.sin(z * 0.093)).astype(np.float32)
+    tv = np.stack([x, y, z], -1).reshape(-1, 3)
+    ddx = np.gradient(y, ext / R, axis=1)
+    ddz = np.gradient(y, ext / R, axis=0)
+    tn = np.stack([-ddx, np.ones_like(ddx), -ddz], -1).reshape(-1, 3)
+    tn /= np.linalg.norm(tn, axis=1, keepdims=True)
+    tt = np.stack([gx / R, gz / R], -1).reshape(-1, 2).astype(np.float32)
+    i0 = (gz[:-1, :-1] * (R + 1) + gx[:-1, :-1]).reshape(-1)
+    i1, i2, i3 = i0 + 1, i0 + (R + 1) + 1, i0 + (R + 1)
+    tf = np.concatenate([np.stack([i0, i3, i2], 1), np.stack([i0, i2, i1], 1)], axis=1).reshape(-1, 3)
+
+    nu, nv = mesh_res
+    uu, vv = np.meshgrid(np.arange(nu + 1), np.arange(nv + 1), indexing="xy")
+    phi = uu.astype(np.float64) / nu * 2 * np.pi
+    theta = vv.astype(np.float64) / nv * np.pi
+    unit = np.stack([np.sin(theta) * np.cos(phi), np.cos(theta), np.sin(theta) * np.sin(phi)], -1).reshape(-1, 3)
+    bump = 1.0 + 0.18 * np.sin(5 * phi).reshape(-1) * np.sin(4 * theta).reshape(-1) ** 2
+    mv = (unit * bump[:, None]).astype(np.float32)
+    mn = unit.astype(np.float32)
+    mt = np.stack([uu / nu, vv / nv], -1).reshape(-1, 2).astype(np.float32)
+    a = (vv[:-1, :-1] * (nu + 1) + uu[:-1, :-1]).reshape(-1)
+    b, c, d = a + 1, a + (nu + 1) + 1, a + (nu + 1)
+    mf = np.concatenate([np.stack([a, b, c], 1), np.stack([a, c, d], 1)], axis=1).reshape(-1, 3)
+
+    n = n_instances
+    nmv, nmf = len(mv), len(mf)
+    verts = np.concatenate([tv, np.tile(mv, (n, 1))])
+    norms = np.concatenate([tn.astype(np.float32), np.tile(mn, (n, 1))])
+    texs = np.concatenate([tt, np.tile(mt, (n, 1))])
+    inst_faces = (np.tile(mf, (n, 1)).reshape(n, nmf, 3) + (len(tv) + np.arange(n) * nmv)[:, None, None])
+    faces = np.concatenate([tf, inst_faces.reshape(-1, 3)]).astype(np.uint32)
+    mats = np.concatenate([np.zeros(len(tf), np.uint32), 1 + (np.repeat(np.arange(n), nmf) % 3).astype(np.uint32)])
+    offsets = np.concatenate([[0], len(tf) + np.arange(n) * nmf]).astype(np.uint32)
+    counts = np.concatenate([[len(tf)], np.full(n, nmf)]).astype(np.uint32)
+    # placements: jittered grid over the terrain, random scale and rotation about y
+    ids = np.arange(n)
+    side = int(np.ceil(np.sqrt(n)))
+    px = ((ids % side + 0.5 + 0.7 * (_hash01(ids * 3 + 1 + seed) - 0.5)) / side - 0.5) * ext * 0.95
+    pz = ((ids // side + 0.5 + 0.7 * (_hash01(ids * 3 + 2 + seed) - 0.5)) / side - 0.5) * ext * 0.95
+    sc = 1.2 + 1.6 * _hash01(ids * 3 + 3 + seed)
+    ang = 2 * np.pi * _hash01(ids + 7919 + seed)
+    py = 6.0 * np.sin(px * 0.031) * np.cos(pz * 0.027) + 2.0 * np.sin(px * 0.11 + 1.3) * np.sin(pz * 0.093) + sc * 0.8
+    tr = np.zeros((n + 1, 4, 4), np.float32)   # column-major: tr[i, col, row]
+    tr[0] = np.eye(4)
+    ca, sa = np.cos(ang) * sc, np.sin(ang) * sc
+    tr[1:, 0, 0], tr[1:, 0, 2] = ca, -sa
+    tr[1:, 1, 1] = sc
+    tr[1:, 2, 0], tr[1:, 2, 2] = sa, ca
+    tr[1:, 3, 0], tr[1:, 3, 1], tr[1:, 3, 2], tr[1:, 3, 3] = px, py, pz, 1.0
+    materials = [make_material(base_color=(0.45, 0.42, 0.38), specular_color=(0, 0, 0)),
+                 make_material(base_color=(0.75, 0.3, 0.25), specular_color=(0, 0, 0)),
+                 make_material(base_color=(0.3, 0.65, 0.35), specular_color=(0, 0, 0)),
+                 make_material(base_color=(0.3, 0.4, 0.8), specular_color=(0, 0, 0))]
+    return SceneArrays(vertices=verts, normals=norms, texcoords=texs, indices=faces, material_ids=mats,
+                       materials=np.array(materials, dtype=MATERIAL_DTYPE), submesh_offsets=offsets,
+                       submesh_n_faces=counts, transforms=tr.reshape(n + 1, 16))
+
+
+INSTANCED_CAMERA = dict(origin=(0.0, 45.0, 230.0), fov=np.deg2rad(55.0), F=100.0, focus=10000.0)
 
 
 STANDARD_CAMERA = dict(origin=(0.0, 6.0, 22.0), fov=np.deg2rad(50.0), F=16.0, focus=20.0)

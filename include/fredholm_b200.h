@@ -151,6 +151,46 @@ int fr_post_process(const void* beauty_in_dev, void* high_luminance_dev, void* t
 int fr_tone_mapping(const void* beauty_in_dev, int width, int height, float ISO, float chromatic_aberration,
                     void* beauty_out_dev);
 
+/* ---- denoise stage: fredholm::Denoiser (fredholm/include/fredholm/denoiser.h:14-145: ctor with the
+ * beauty / normal / albedo / output device pointers, denoise(), wait_for_completion()).  The OptiX AI
+ * denoiser is replaced by an albedo/normal-guided a-trous wavelet filter (include/fredholm/denoiser.h).
+ * One-shot form: construct, denoise, wait.  Output is width x height float4 (2x each with upscale).
+ * iterations <= 0 or sigmas / floor <= 0 select the defaults (5, 0.5, 0.1, 0.01); firefly_k < 0 selects
+ * the default (2), 0 switches the firefly clamp off. */
+int fr_denoise(const void* beauty_dev, const void* normal_dev, const void* albedo_dev, void* denoised_dev,
+               uint32_t width, uint32_t height, int upscale, int iterations, float sigma_color, float sigma_albedo,
+               float albedo_floor, float firefly_k);
+
+/* ---- multi-frame batch: the render / save loop of app/rtcamp8.cpp:47-303 as a library call
+ * (include/fredholm/batch.h).  Per frame: clear layers, init_render_states, set_time(t), render,
+ * denoise, post-process, RGBA8 conversion, read-back, "<output_dir>/<frame>.png". */
+typedef struct fr_batch_config {
+  uint32_t width, height, n_spp, max_depth;   /* rtcamp8.cpp:47-54 */
+  fr_post_process_params post;                /* rtcamp8.cpp:55-58,201-206 */
+  int denoise, upscale;                       /* rtcamp8.cpp:48,113-118 */
+  int dn_iterations;                          /* <= 0: default */
+  float dn_sigma_color, dn_sigma_albedo, dn_albedo_floor, dn_firefly_k; /* as for fr_denoise */
+  float fps, start_time, max_time, kill_time_s; /* rtcamp8.cpp:59-62 */
+  uint32_t first_frame, frame_stride, max_frames; /* multi-GPU: rank, world size */
+  float bg_color[3];
+  int animate;                                /* call set_time every frame */
+  const char* output_dir;                     /* NULL or "": no files */
+  uint32_t n_save_threads, n_slots;
+} fr_batch_config;
+
+typedef struct fr_frame_record {
+  uint32_t frame_idx;
+  float time, accel_ms, render_ms, denoise_ms, post_ms, transfer_ms, encode_ms, save_ms;
+  uint64_t png_bytes;
+} fr_frame_record;
+
+/* camera: one 3x4 block (n_camera_frames = 0) or a path of n_camera_frames blocks indexed by
+ * min(frame_idx, n_camera_frames - 1).  records: room for max_records entries; frames_rgba8 (optional):
+ * max_records x out_w x out_h x 4 bytes, filled in record order.  out5 = n_records, out_w, out_h, killed, 0. */
+int fr_batch_run(fr_renderer* r, const fr_batch_config* config, const float* camera_transforms12,
+                 uint32_t n_camera_frames, float fov, float F, float focus, fr_frame_record* records,
+                 uint32_t max_records, uint8_t* frames_rgba8, uint32_t* out5, double* wall_s);
+
 /* ---- raw device memory helpers (cwl::CUDABuffer, buffer.h:18-85) ---- */
 void* fr_device_alloc(size_t bytes);
 int fr_device_free(void* p);
