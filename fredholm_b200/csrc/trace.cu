@@ -23,6 +23,9 @@ namespace
 {
 
 constexpr int kBlock = 128;
+#ifndef FRD_TRACE_BLOCKS
+#define FRD_TRACE_BLOCKS 8  // resident CTAs per SM: 64 registers per thread
+#endif
 
 // alpha cut-out: candidate is ignored if base-colour alpha or the alpha map is < 0.5
 struct AlphaTest {
@@ -82,7 +85,7 @@ struct ClosestPolicy {
   }
 };
 
-__global__ void __launch_bounds__(kBlock, 8) k_trace_closest(SceneView sc, WaveBuffers wb, uint32_t depth, int refill, int tri_lanes,
+__global__ void __launch_bounds__(kBlock, FRD_TRACE_BLOCKS) k_trace_closest(SceneView sc, WaveBuffers wb, uint32_t depth, int refill, int tri_lanes,
                                                              const uint32_t* order)
 {
   FR_DECLARE_STACK();
@@ -123,7 +126,7 @@ struct ShadowPolicy {
   }
 };
 
-__global__ void __launch_bounds__(kBlock, 8) k_trace_shadow(SceneView sc, WaveBuffers wb, int which, int refill, int tri_lanes,
+__global__ void __launch_bounds__(kBlock, FRD_TRACE_BLOCKS) k_trace_shadow(SceneView sc, WaveBuffers wb, int which, int refill, int tri_lanes,
                                                             const uint32_t* order)
 {
   FR_DECLARE_STACK();
@@ -202,7 +205,7 @@ struct LightPolicy {
 
 // (scenes without any emissive face never get here: their MIS rays are visibility rays with
 // the sky contribution precomputed by the shade stage, traced by k_trace_shadow)
-__global__ void __launch_bounds__(kBlock, 8) k_trace_light(SceneView sc, WaveBuffers wb, int refill, int tri_lanes,
+__global__ void __launch_bounds__(kBlock, FRD_TRACE_BLOCKS) k_trace_light(SceneView sc, WaveBuffers wb, int refill, int tri_lanes,
                                                            const uint32_t* order)
 {
   FR_DECLARE_STACK();

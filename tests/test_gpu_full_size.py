@@ -50,7 +50,13 @@ def test_accel_build(big):
     assert info["n_faces"] == s.n_faces
     assert 0 < info["n_nodes"] < s.n_faces          # 8-wide: far fewer nodes than triangles
     assert info["depth"] <= 48                       # traversal stack bound (bvh.cuh)
-    assert info["build_ms"] < 1000.0
+    # the first build of a process also pays lazy module loading and the first big allocations;
+    # the steady-state figure is the second build (11 ms in profiles/)
+    assert info["build_ms"] < 10000.0
+    r.build_accel()
+    again = r.accel_info()
+    assert again["n_nodes"] == info["n_nodes"] and again["depth"] == info["depth"]
+    assert again["build_ms"] < 500.0
 
 
 def test_primary_hits_match_oracle_1080p(big, oracle):
