@@ -146,7 +146,10 @@ FR_D float byte_f(uint32_t w, int j) { return (float)((w >> (8 * j)) & 0xffu); }
 
 // Short stack kept in shared memory (one column per thread, 8-byte entries, so a
 // warp's accesses are conflict free); deep paths overflow to thread-local memory.
-constexpr int kSmemStack = 12;
+#ifndef FRD_SMEM_STACK
+#define FRD_SMEM_STACK 12
+#endif
+constexpr int kSmemStack = FRD_SMEM_STACK;
 constexpr int kLocalStack = 36;
 
 struct TravStack {

@@ -7,6 +7,12 @@
 // tree is rebuilt, not refitted, when transforms change -- a full build of 1 M
 // triangles is a few milliseconds on a B200.
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_select.cuh>
+
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
 
 #include "bvh_build.h"
 
@@ -131,6 +137,8 @@ struct Lbvh {
   float4* lo;          // [2n-1]
   float4* hi;          // [2n-1]
   uint32_t* visit;     // [n-1]
+  const uint32_t* leaf_pos;  // [n] position of sorted leaf j in the triangle order the collapse reads
+                             // (null: the Morton order itself, LBVH)
 };
 
 __device__ __forceinline__ int delta(const uint64_t* keys, int n, int i, int j)
@@ -204,6 +212,144 @@ __global__ void k_fit(const float4* __restrict__ wtri, const uint32_t* __restric
   }
 }
 
+
+// ---- stage 3b/4b (alternative): PLOC, parallel locally-ordered clustering ------------------
+// Meister & Bittner 2018.  Bottom-up agglomerative build over the Morton-ordered clusters: every
+// cluster looks `radius` positions to either side for the neighbour that gives the smallest
+// merged box, mutual nearest neighbours merge, the cluster array is compacted (order kept) and
+// the round repeats until one cluster is left.  Tree quality is close to a full SAH sweep (the
+// host-SAH bound in profiles/r1_bvh_collapse_experiment.txt) at a few ms per million triangles.
+// Node ids follow the LBVH convention (internal 0..n-2 with the root at 0, leaf j at n-1+j), so
+// the 8-wide collapse below serves both builders; internal ids are handed out downwards from
+// n-2 so that the last merge -- the root -- gets id 0.
+constexpr uint32_t kInvalidCluster = 0xffffffffu;
+constexpr int kPlocBlock = 256;
+constexpr int kPlocMaxRadius = 32;
+
+__global__ void k_leaf_boxes(const float4* __restrict__ wtri, const uint32_t* __restrict__ sorted, int n, Lbvh t,
+                             uint32_t* __restrict__ clusters)
+{
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const uint32_t f = sorted[j];
+  const float4 a = wtri[3ull * f], b = wtri[3ull * f + 1], c = wtri[3ull * f + 2];
+  const uint32_t leaf = n - 1 + j;
+  t.lo[leaf] = make_float4(fminf(fminf(a.x, b.x), c.x), fminf(fminf(a.y, b.y), c.y), fminf(fminf(a.z, b.z), c.z), 0.0f);
+  t.hi[leaf] = make_float4(fmaxf(fmaxf(a.x, b.x), c.x), fmaxf(fmaxf(a.y, b.y), c.y), fmaxf(fmaxf(a.z, b.z), c.z), 0.0f);
+  clusters[j] = leaf;
+}
+
+__global__ void __launch_bounds__(kPlocBlock) k_ploc_nearest(const uint32_t* __restrict__ clusters, uint32_t c, int radius, Lbvh t,
+                                                             uint32_t* __restrict__ nearest)
+{
+  __shared__ float s_lo[kPlocBlock + 2 * kPlocMaxRadius][3];
+  __shared__ float s_hi[kPlocBlock + 2 * kPlocMaxRadius][3];
+  const int base = (int)(blockIdx.x * kPlocBlock) - radius;
+  for (int k = threadIdx.x; k < kPlocBlock + 2 * radius; k += kPlocBlock) {
+    const int g = base + k;
+    if (g >= 0 && g < (int)c) {
+      const uint32_t id = clusters[g];
+      const float4 l = t.lo[id], h = t.hi[id];
+      s_lo[k][0] = l.x, s_lo[k][1] = l.y, s_lo[k][2] = l.z;
+      s_hi[k][0] = h.x, s_hi[k][1] = h.y, s_hi[k][2] = h.z;
+    }
+  }
+  __syncthreads();
+  const int i = blockIdx.x * kPlocBlock + threadIdx.x;
+  if (i >= (int)c) return;
+  const int me = threadIdx.x + radius;
+  const float lx = s_lo[me][0], ly = s_lo[me][1], lz = s_lo[me][2];
+  const float hx = s_hi[me][0], hy = s_hi[me][1], hz = s_hi[me][2];
+  // The key (merged area, pair hash) is symmetric in (i, j) bit for bit, so the pair with the globally
+  // smallest key is always mutual (progress).  The hash breaks the area ties of regular meshes: with
+  // "lower index wins" every cluster of a regular grid would point at its left neighbour and only
+  // one pair per round would merge.
+  unsigned long long best = ~0ull;
+  int best_j = -1;
+  const int j0 = max(i - radius, 0), j1 = min(i + radius, (int)c - 1);
+  for (int j = j0; j <= j1; ++j) {
+    if (j == i) continue;
+    const int k = j - base;
+    const float ex = fmaxf(hx, s_hi[k][0]) - fminf(lx, s_lo[k][0]);
+    const float ey = fmaxf(hy, s_hi[k][1]) - fminf(ly, s_lo[k][1]);
+    const float ez = fmaxf(hz, s_hi[k][2]) - fminf(lz, s_lo[k][2]);
+    const float a = ex * ey + ey * ez + ez * ex;
+    uint32_t h = (uint32_t)min(i, j) * 0x9E3779B1u ^ (uint32_t)max(i, j) * 0x85EBCA77u;
+    h ^= h >> 15;
+    h *= 0x2C1B3C6Du;
+    h ^= h >> 13;
+    const unsigned long long key = ((unsigned long long)__float_as_uint(a) << 32) | h;  // a >= 0
+    if (key < best) {
+      best = key;
+      best_j = j;
+    }
+  }
+  nearest[i] = (uint32_t)best_j;
+}
+
+__global__ void k_ploc_merge(const uint32_t* __restrict__ clusters, uint32_t c, const uint32_t* __restrict__ nearest,
+                             int n, Lbvh t, uint32_t* __restrict__ n_merged, uint32_t* __restrict__ out)
+{
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= c) return;
+  const uint32_t j = nearest[i];
+  const uint32_t a = clusters[i];
+  if (j < c && nearest[j] == i) {
+    if (i < j) {
+      const uint32_t b = clusters[j];
+      const uint32_t id = (uint32_t)(n - 2) - atomicAdd(n_merged, 1u);
+      t.child[id] = make_uint2(a, b);
+      t.parent[a] = id;
+      t.parent[b] = id;
+      const float4 la = t.lo[a], lb = t.lo[b], ha = t.hi[a], hb = t.hi[b];
+      t.lo[id] = make_float4(fminf(la.x, lb.x), fminf(la.y, lb.y), fminf(la.z, lb.z), 0.0f);
+      t.hi[id] = make_float4(fmaxf(ha.x, hb.x), fmaxf(ha.y, hb.y), fmaxf(ha.z, hb.z), 0.0f);
+      const uint32_t ca = a >= (uint32_t)(n - 1) ? 1u : t.visit[a];
+      const uint32_t cb = b >= (uint32_t)(n - 1) ? 1u : t.visit[b];
+      t.visit[id] = ca + cb;  // triangles below the node (the LBVH fit counter is free here)
+      out[i] = id;
+    } else {
+      out[i] = kInvalidCluster;
+    }
+  } else {
+    out[i] = a;
+  }
+}
+
+struct ValidCluster {
+  __device__ __forceinline__ bool operator()(const uint32_t& v) const { return v != kInvalidCluster; }
+};
+
+// Left-to-right position of the first triangle under `id`: walk to the root adding the sizes of
+// the left siblings passed on the way.  Gives every sub-tree a contiguous triangle range.
+__device__ __forceinline__ uint32_t ploc_first(const Lbvh& t, int n, uint32_t id)
+{
+  uint32_t first = 0;
+  uint32_t cur = id;
+  for (;;) {
+    const uint32_t p = t.parent[cur];
+    if (p == 0xffffffffu) break;
+    const uint2 ch = t.child[p];
+    if (ch.y == cur) first += ch.x >= (uint32_t)(n - 1) ? 1u : t.visit[ch.x];
+    cur = p;
+  }
+  return first;
+}
+
+__global__ void k_ploc_ranges(int n, Lbvh t, const uint32_t* __restrict__ sorted, uint32_t* __restrict__ leaf_pos,
+                              uint32_t* __restrict__ order)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 2 * n - 1) return;
+  const uint32_t first = ploc_first(t, n, (uint32_t)i);
+  if (i < n - 1) {
+    t.range[i] = make_uint2(first, first + t.visit[i] - 1u);
+  } else {
+    leaf_pos[i - (n - 1)] = first;
+    order[first] = sorted[i - (n - 1)];
+  }
+}
+
 // ---- stage 5: collapse to 8-wide + quantise --------------------------------------------------
 __device__ __forceinline__ uint32_t tri_count(const Lbvh& t, int n, uint32_t id)
 {
@@ -213,7 +359,8 @@ __device__ __forceinline__ uint32_t tri_count(const Lbvh& t, int n, uint32_t id)
 }
 __device__ __forceinline__ uint32_t first_leaf(const Lbvh& t, int n, uint32_t id)
 {
-  return id >= (uint32_t)(n - 1) ? id - (uint32_t)(n - 1) : t.range[id].x;
+  if (id >= (uint32_t)(n - 1)) return t.leaf_pos ? t.leaf_pos[id - (uint32_t)(n - 1)] : id - (uint32_t)(n - 1);
+  return t.range[id].x;
 }
 __device__ __forceinline__ float half_area(const float4& lo, const float4& hi)
 {
@@ -406,6 +553,38 @@ __global__ void k_empty_root(Node8* nodes)
   nodes[0] = out;
 }
 
+// builder selection (experiments / fallback): FRD_BVH_BUILDER=lbvh|ploc, FRD_PLOC_RADIUS=1..32
+bool builder_is_ploc()
+{
+  const char* e = getenv("FRD_BVH_BUILDER");
+  return !(e && strcmp(e, "lbvh") == 0);
+}
+int ploc_radius()
+{
+  const char* e = getenv("FRD_PLOC_RADIUS");
+  const int r = e ? atoi(e) : 16;
+  return r < 1 ? 1 : (r > kPlocMaxRadius ? kPlocMaxRadius : r);
+}
+
+}  // namespace
+
+namespace
+{
+// FRD_BVH_VERBOSE=1: host wall time per build phase (synchronises at every mark)
+struct PhaseClock {
+  bool on = getenv("FRD_BVH_VERBOSE") != nullptr;
+  cudaStream_t s;
+  std::chrono::steady_clock::time_point t0;
+  explicit PhaseClock(cudaStream_t st) : s(st), t0(std::chrono::steady_clock::now()) {}
+  void mark(const char* what)
+  {
+    if (!on) return;
+    cudaStreamSynchronize(s);
+    const auto t1 = std::chrono::steady_clock::now();
+    fprintf(stderr, "[bvh] %-10s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+    t0 = t1;
+  }
+};
 }  // namespace
 
 void build_bvh(cudaStream_t stream, const float3* d_vertices, const uint3* d_indices,
@@ -427,6 +606,7 @@ void build_bvh(cudaStream_t stream, const float3* d_vertices, const uint3* d_ind
   const int B = 256;
   const int G = (n + B - 1) / B;
 
+  PhaseClock clk(stream);
   DevBuf<float4> wtri(3ull * n);
   DevBuf<float> bounds(6);
   const float init_b[6] = {3.0e38f, 3.0e38f, 3.0e38f, -3.0e38f, -3.0e38f, -3.0e38f};
@@ -446,19 +626,66 @@ void build_bvh(cudaStream_t stream, const float3* d_vertices, const uint3* d_ind
   FR_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(tmp.get(), tmp_bytes, keys.get(), keys_sorted.get(), vals.get(),
                                                 sorted.get(), n, 0, 63, stream));
 
+  clk.mark("sort");
   const int n_int = n > 1 ? n - 1 : 1;
   DevBuf<uint2> child(n_int), range(n_int);
   DevBuf<uint32_t> parent(2ull * n), visit(n_int);
   DevBuf<float4> lo(2ull * n), hi(2ull * n);
   visit.zero(stream);
-  Lbvh t{child.get(), parent.get(), range.get(), lo.get(), hi.get(), visit.get()};
-  if (n > 1) {
-    k_karras<<<(n - 1 + B - 1) / B, B, 0, stream>>>(keys_sorted.get(), n, t);
+  Lbvh t{child.get(), parent.get(), range.get(), lo.get(), hi.get(), visit.get(), nullptr};
+  DevBuf<uint32_t> leaf_pos, order;
+  const uint32_t* tri_order = sorted.get();
+  out.ploc_rounds = 0;
+  if (builder_is_ploc() && n > 2) {
+    // ---- PLOC ----
+    const int radius = ploc_radius();
+    DevBuf<uint32_t> cl_a(n), cl_b(n), nearest(n), counters2(2);
+    counters2.zero(stream);
+    uint32_t* n_merged = counters2.get();
+    uint32_t* n_selected = counters2.get() + 1;
+    clk.mark("ploc alloc");
+    k_leaf_boxes<<<G, B, 0, stream>>>(wtri.get(), sorted.get(), n, t, cl_a.get());
+    FR_CUDA_LAUNCH_CHECK();
+    size_t sel_bytes = 0;
+    FR_CUDA_CHECK(cub::DeviceSelect::If(nullptr, sel_bytes, cl_b.get(), cl_a.get(), n_selected, n, ValidCluster{}, stream));
+    DevBuf<unsigned char> sel_tmp(sel_bytes);
+    uint32_t c = (uint32_t)n;
+    uint32_t* cur = cl_a.get();
+    uint32_t* nxt = cl_b.get();
+    while (c > 1) {
+      const int g = (int)((c + kPlocBlock - 1) / kPlocBlock);
+      k_ploc_nearest<<<g, kPlocBlock, 0, stream>>>(cur, c, radius, t, nearest.get());
+      k_ploc_merge<<<g, kPlocBlock, 0, stream>>>(cur, c, nearest.get(), n, t, n_merged, nxt);
+      FR_CUDA_LAUNCH_CHECK();
+      // compact (order kept) back into `cur`
+      FR_CUDA_CHECK(cub::DeviceSelect::If(sel_tmp.get(), sel_bytes, nxt, cur, n_selected, (int)c, ValidCluster{}, stream));
+      uint32_t c_next = 0;
+      FR_CUDA_CHECK(cudaMemcpyAsync(&c_next, n_selected, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+      FR_CUDA_CHECK(cudaStreamSynchronize(stream));
+      if (c_next >= c) throw std::runtime_error("bvh ploc: no progress");
+      c = c_next;
+      out.ploc_rounds++;
+    }
+    clk.mark("ploc loop");
+    if (getenv("FRD_BVH_VERBOSE")) fprintf(stderr, "[bvh] ploc radius %d: %u rounds\n", radius, out.ploc_rounds);
+    const uint32_t none = 0xffffffffu;
+    FR_CUDA_CHECK(cudaMemcpyAsync(parent.get(), &none, sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+    leaf_pos.alloc(n);
+    order.alloc(n);
+    k_ploc_ranges<<<(2 * n - 1 + B - 1) / B, B, 0, stream>>>(n, t, sorted.get(), leaf_pos.get(), order.get());
+    FR_CUDA_LAUNCH_CHECK();
+    t.leaf_pos = leaf_pos.get();
+    tri_order = order.get();
+  } else {
+    if (n > 1) {
+      k_karras<<<(n - 1 + B - 1) / B, B, 0, stream>>>(keys_sorted.get(), n, t);
+      FR_CUDA_LAUNCH_CHECK();
+    }
+    k_fit<<<G, B, 0, stream>>>(wtri.get(), sorted.get(), n, t);
     FR_CUDA_LAUNCH_CHECK();
   }
-  k_fit<<<G, B, 0, stream>>>(wtri.get(), sorted.get(), n, t);
-  FR_CUDA_LAUNCH_CHECK();
 
+  clk.mark("binary");
   // collapse, level by level; node n8 is built from binary node work[n8]
   const size_t max_nodes = (size_t)n / 2 + 2;
   DevBuf<Node8> nodes(max_nodes);
@@ -472,7 +699,7 @@ void build_bvh(cudaStream_t stream, const float3* d_vertices, const uint3* d_ind
   uint32_t begin = 0, end = 1, depth = 0;
   while (begin < end) {
     const uint32_t cnt = end - begin;
-    k_collapse<<<(cnt + 63) / 64, 64, 0, stream>>>(begin, end, work.get(), n, t, wtri.get(), sorted.get(),
+    k_collapse<<<(cnt + 63) / 64, 64, 0, stream>>>(begin, end, work.get(), n, t, wtri.get(), tri_order,
                                                     counters.get(), nodes.get(), out.tris.get());
     FR_CUDA_LAUNCH_CHECK();
     CollapseCounters h;
@@ -483,6 +710,7 @@ void build_bvh(cudaStream_t stream, const float3* d_vertices, const uint3* d_ind
     end = h.n_nodes;
     depth++;
   }
+  clk.mark("collapse");
   out.depth = depth;
   out.n_nodes = end;
   // shrink the node pool to its final size
@@ -495,6 +723,7 @@ void build_bvh(cudaStream_t stream, const float3* d_vertices, const uint3* d_ind
     out.bounds_lo[a] = hb[a];
     out.bounds_hi[a] = hb[3 + a];
   }
+  clk.mark("finish");
   if (depth + 2 > (uint32_t)(kSmemStack + kLocalStack))
     throw std::runtime_error("bvh: tree too deep for the traversal stack");
 }

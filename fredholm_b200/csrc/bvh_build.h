@@ -15,6 +15,7 @@ struct DeviceBvh {
   uint32_t n_nodes = 0;
   uint32_t n_faces = 0;
   uint32_t depth = 0;  // levels of the 8-wide tree
+  uint32_t ploc_rounds = 0;  // merge rounds of the PLOC builder (0: LBVH)
   float bounds_lo[3] = {0, 0, 0}, bounds_hi[3] = {0, 0, 0};
 
   BvhView view() const

@@ -13,7 +13,8 @@ a = ap.parse_args()
 s = scenes.standard_surface_scene()
 L = scenes.STANDARD_LIGHTING; C = scenes.STANDARD_CAMERA
 cam = Camera(api.camera_walk(C["origin"], 0.0, 150.0, 0, 0.0), C["fov"], C["F"], C["focus"])
-r = Renderer(0); r.set_scene(s); r.build_accel()
+r = Renderer(0); r.set_scene(s); r.build_accel(); r.build_accel()
+print("accel", r.accel_info())
 r.set_directional_light(L["sun_le"], L["sun_dir"], L["sun_angle"]); r.load_arhosek_sky(L["turbidity"], L["albedo"])
 W, H = 1920, 1080
 r.set_resolution(W, H)
