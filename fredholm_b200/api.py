@@ -454,6 +454,10 @@ class Renderer:
         assert img.ndim == 3 and img.shape[2] == 4
         _check(lib().fr_set_ibl(self._h, _f(img), img.shape[1], img.shape[0]))
 
+    def load_ibl(self, path):
+        """Renderer::load_ibl (renderer.h:574-583): Radiance .hdr file, not flipped."""
+        _check(lib().fr_load_ibl(self._h, os.fsencode(str(path))))
+
     def clear_ibl(self):
         _check(lib().fr_clear_ibl(self._h))
 

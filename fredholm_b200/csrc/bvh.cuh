@@ -370,11 +370,14 @@ FR_D void trace_queue(const BvhView& bvh, Policy& pol, uint32_t* cursor, uint32_
   for (;;) {
     const uint32_t idle = __ballot_sync(0xffffffffu, !have);
     if (idle == 0xffffffffu || (!exhausted && __popc(idle) >= refill_lanes)) {
+      // the cursor atomic is issued first and consumed after the retire step, so that its round
+      // trip overlaps the retire step's own memory traffic (queue appends, radiance updates)
+      const bool fetch = !exhausted;
+      uint32_t base = 0;
+      if (fetch && lane == 0) base = atomicAdd(cursor, (uint32_t)__popc(idle));
       pol.retire(finished, tr.best, cnt);
       finished = false;
-      if (!exhausted) {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(cursor, (uint32_t)__popc(idle));
+      if (fetch) {
         base = __shfl_sync(0xffffffffu, base, 0);
         const uint32_t item = base + __popc(idle & ((1u << lane) - 1u));
         if (!have && item < n) {

@@ -72,15 +72,17 @@ struct ClosestPolicy {
       // a miss only needs work for camera rays (sky seen directly, pt.cu:504-523)
       cls = h.face != kNoHit ? (int)sc.face_class[h.face] : (depth == 0 ? (int)CLS_MISS : -1);
     }
-    // append the path to the shade queue of the class it hit (one atomic per class
-    // present among the retiring lanes)
-    uint32_t todo = __ballot_sync(0xffffffffu, cls >= 0);
-    while (todo) {
-      const int c = __shfl_sync(0xffffffffu, cls, __ffs(todo) - 1);
-      const bool mine = cls == c;
-      const uint32_t pos = queue_reserve(&wb.ctl->n_class[c], mine);
-      if (mine) wb.class_queue[c][pos] = slot;
-      todo &= ~__ballot_sync(0xffffffffu, mine);
+    // append the path to the shade queue of the class it hit: the retiring lanes group by class
+    // (match_any), the first lane of every group reserves for its group, and all groups' atomics
+    // are in flight together -- one round trip however many classes the warp retires
+    const uint32_t appending = __ballot_sync(0xffffffffu, cls >= 0);
+    if (cls >= 0) {
+      const uint32_t peers = __match_any_sync(appending, cls);
+      const int leader = __ffs(peers) - 1;
+      uint32_t base = 0;
+      if ((int)lane_id() == leader) base = atomicAdd(&wb.ctl->n_class[cls], (uint32_t)__popc(peers));
+      base = __shfl_sync(peers, base, leader);
+      wb.class_queue[cls][base + __popc(peers & ((1u << lane_id()) - 1u))] = slot;
     }
   }
 };
