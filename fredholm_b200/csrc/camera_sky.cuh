@@ -101,10 +101,12 @@ enum SkyMode : int { SKY_CONSTANT = 0, SKY_HOSEK = 1, SKY_IBL = 2 };
 // exactly as in the reference -- callers rely on the NaN guard of the film stage.
 FR_D float3 hosek_radiance(const HosekSky& s, const float3& v, const float3& sun_dir)
 {
-  const float theta = acosf(clampf(v.y, -1.0f, 1.0f));
-  const float gamma = acosf(dot(sun_dir, v));
-  const float cg = cosf(gamma);
-  const float ct = cosf(theta);
+  // cos(theta) and cos(gamma) are the dot products themselves (the reference takes acos and then
+  // cos again, arhosek.cu:103-127; equal to an ulp), and x^1.5 is x * sqrt(x): the three powf calls
+  // were 7 % of the shade stage's instructions (profiles/r1i_shade_lines_1.txt)
+  const float ct = clampf(v.y, -1.0f, 1.0f);
+  const float cg = dot(sun_dir, v);
+  const float gamma = acosf(cg);  // NaN for |cg| > 1, as in the reference
   const float ray_m = cg * cg;
   const float zenith = sqrtf(ct);
   float out[3];
@@ -112,7 +114,8 @@ FR_D float3 hosek_radiance(const HosekSky& s, const float3& v, const float3& sun
   for (int c = 0; c < 3; ++c) {
     const float* k = s.cfg[c];
     const float exp_m = expf(k[4] * gamma);
-    const float mie_m = (1.0f + cg * cg) / powf(1.0f + k[8] * k[8] - 2.0f * k[8] * cg, 1.5f);
+    const float x = 1.0f + k[8] * k[8] - 2.0f * k[8] * cg;
+    const float mie_m = (1.0f + cg * cg) / (x * sqrtf(x));
     out[c] = (1.0f + k[0] * expf(k[1] / (ct + 0.01f))) *
              (k[2] + k[3] * exp_m + k[5] * ray_m + k[6] * mie_m + k[7] * zenith) * s.rad[c];
   }
