@@ -159,6 +159,7 @@ void Integrator::render(const SceneView& scene, const fredholm::CameraParams& ca
     wp.sample_base = sample_base + done;
     wp.max_depth = max_depth;
     wp.seed = seed;
+    wp.want_aov = (layers.position || layers.normal || layers.depth || layers.texcoord || layers.albedo) ? 1u : 0u;
     wp.camera = camera;
 
     stage(STAGE_ADVANCE, [&] { launch_wave_begin(m_stream, wb, (unsigned long long)wp.n_samples * width * height); });

@@ -54,9 +54,11 @@ __global__ void __launch_bounds__(kBlock) k_generate(WaveParams wp, WaveBuffers 
     uint32_t x, y;
     const bool inside = slot_to_pixel(wp.film, slot % wp.film.slots_per_sample, x, y);
     wb.L[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
-    wb.aov0[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
-    wb.aov1[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
-    wb.aov2[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (wp.want_aov) {  // the first-hit words are only kept when a layer will read them
+      wb.aov0[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
+      wb.aov1[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
+      wb.aov2[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     if (inside && wp.max_depth > 0) {
       PathSampler s;
       s.init(x + wp.film.width * y, wp.sample_base + slot / wp.film.slots_per_sample,
@@ -238,9 +240,11 @@ __global__ void __launch_bounds__(kBlock, FRD_SHADE_BLOCKS) k_shade(WaveParams w
 
       if (depth == 0) {
         // first-hit AOVs and directly visible emitters (pt.cu:745-760)
-        wb.aov0[slot] = make_float4(x.x, x.y, x.z, hit.x);
-        wb.aov1[slot] = make_float4(fr.n.x, fr.n.y, fr.n.z, uv.x);
-        wb.aov2[slot] = make_float4(sp.base_color.x, sp.base_color.y, sp.base_color.z, uv.y);
+        if (wp.want_aov) {
+          wb.aov0[slot] = make_float4(x.x, x.y, x.z, hit.x);
+          wb.aov1[slot] = make_float4(fr.n.x, fr.n.y, fr.n.z, uv.x);
+          wb.aov2[slot] = make_float4(sp.base_color.x, sp.base_color.y, sp.base_color.z, uv.y);
+        }
         if (is_emissive(mat)) {
           const float3 le = TEX ? emission_of(mat, tex, uv) : mat.emission_color;
           add_radiance(wb, slot, throughput * le);
@@ -435,7 +439,8 @@ __global__ void __launch_bounds__(256) k_film(WaveParams wp, WaveBuffers wb, fre
     const float4 L = wb.L[slot];
     float3 radiance = f3(L);
     if (bad3(radiance)) radiance = f3(0.f);  // pt.cu:475-478
-    const float4 a0 = wb.aov0[slot], a1 = wb.aov1[slot], a2 = wb.aov2[slot];
+    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0;
+    if (wp.want_aov) a0 = wb.aov0[slot], a1 = wb.aov1[slot], a2 = wb.aov2[slot];
     if (film_mode == FILM_MEAN) {
       const float nf = (float)n_spp;
       const float coef = 1.0f / (nf + 1.0f);

@@ -167,6 +167,7 @@ struct WaveParams {
   uint32_t sample_base;  // sample index of the first one (reference: sample_count)
   uint32_t max_depth;
   uint32_t seed;
+  uint32_t want_aov;     // any first-hit layer (position / normal / depth / texcoord / albedo) is bound
   fredholm::CameraParams camera;
 };
 
