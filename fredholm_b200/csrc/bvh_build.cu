@@ -454,6 +454,9 @@ __global__ void k_collapse(uint32_t level_begin, uint32_t level_end, uint32_t* _
       cost[k][s] = ((s & 1) ? dc.x : -dc.x) + ((s & 2) ? dc.y : -dc.y) + ((s & 4) ? dc.z : -dc.z);
     }
   }
+  // nodes with at most four children keep them in slots 0-3 (ordered along x and y only), so that
+  // the traversal can skip the empty upper half of the node test (bvh.cuh, node_phase)
+  const int n_slots = nc <= 4 ? 4 : 8;
   int slot_of[8];
   int child_at[8];
   for (int s = 0; s < 8; ++s) child_at[s] = -1;
@@ -463,7 +466,7 @@ __global__ void k_collapse(uint32_t level_begin, uint32_t level_end, uint32_t* _
     float bc = -3.0e38f;
     for (int k = 0; k < nc; ++k) {
       if (slot_of[k] >= 0) continue;
-      for (int s = 0; s < 8; ++s) {
+      for (int s = 0; s < n_slots; ++s) {
         if (child_at[s] >= 0) continue;
         if (cost[k][s] > bc) {
           bc = cost[k][s];
