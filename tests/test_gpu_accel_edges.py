@@ -1,0 +1,195 @@
+"""Acceleration-structure edge cases on the GPU: both builders, tiny and
+degenerate inputs, exact t ties, instance transforms and alpha cut-outs -- (instance, primitive) and the
+bits of t/u/v against the host oracle's traversal, which itself is pinned on a brute-force loop
+(tests/test_oracle_golden.py::test_traversal_matches_bruteforce)."""
+import os
+
+import numpy as np
+import pytest
+
+from fredholm_b200 import Camera, DeviceLayers, api, scenes
+from fredholm_b200.scenes import _assemble, _quad
+from fredholm_b200.types import make_material
+
+pytestmark = pytest.mark.gpu
+
+MISS = 0xffffffff
+
+
+def random_rays(n, seed, lo=-3.0, hi=3.0):
+    rng = np.random.default_rng(seed)
+    o = rng.uniform(lo, hi, (n, 3)).astype(np.float32)
+    d = rng.normal(size=(n, 3)).astype(np.float32)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    return np.concatenate([o, d], 1).astype(np.float32)
+
+
+def rays_at(targets, seed):
+    """Rays from random origins through given points (so that small scenes are actually hit)."""
+    rng = np.random.default_rng(seed)
+    t = np.asarray(targets, np.float32)
+    o = t + rng.normal(size=t.shape).astype(np.float32) * 2.0
+    d = t - o
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    return np.concatenate([o, d], 1).astype(np.float32)
+
+
+def both(renderer, oracle, scene, rays):
+    renderer.set_scene(scene)
+    renderer.build_accel()
+    oracle.set_scene(scene)
+    oracle.build_accel()
+    ids_g, tuv_g = renderer.trace_closest(rays)
+    ids_o, tuv_o = oracle.trace_closest(rays)
+    return ids_g, tuv_g, ids_o, tuv_o
+
+
+def assert_identical(ids_g, tuv_g, ids_o, tuv_o, min_hits=1):
+    assert np.array_equal(ids_g, ids_o)
+    hit = ids_o[:, 0] != MISS
+    assert hit.sum() >= min_hits
+    assert np.array_equal(tuv_g[hit].view(np.uint32), tuv_o[hit].view(np.uint32))
+
+
+def soup(n, seed, size=0.4):
+    rng = np.random.default_rng(seed)
+    c = rng.uniform(-2, 2, (n, 1, 3))
+    p = (c + rng.normal(size=(n, 3, 3)) * size).astype(np.float32)
+    mat = make_material(base_color=(0.7, 0.7, 0.7))
+    return _assemble([[(tri, 0) for tri in p]], [mat]), p
+
+
+@pytest.mark.parametrize("builder", ["lbvh", "ploc"])
+def test_builders_agree_with_oracle(renderer, oracle, builder, monkeypatch):
+    monkeypatch.setenv("FRD_BVH_BUILDER", builder)
+    s = scenes.standard_surface_scene(48, 24, sphere_res=(12, 6))
+    rays = random_rays(60000, 11, -12, 12)
+    rays[:, 1] = np.abs(rays[:, 1]) * 0.4 + 0.2
+    ids_g, tuv_g, ids_o, tuv_o = both(renderer, oracle, s, rays)
+    assert_identical(ids_g, tuv_g, ids_o, tuv_o, min_hits=10000)
+    info = renderer.accel_info()
+    assert info["n_faces"] == s.n_faces and info["n_nodes"] >= 1
+
+
+@pytest.mark.parametrize("radius", ["1", "3", "32"])
+def test_ploc_radius_extremes(renderer, oracle, radius, monkeypatch):
+    monkeypatch.setenv("FRD_BVH_BUILDER", "ploc")
+    monkeypatch.setenv("FRD_PLOC_RADIUS", radius)
+    s, p = soup(3000, 5)
+    rays = np.concatenate([rays_at(p.mean(axis=1), 6), random_rays(20000, 7)])
+    assert_identical(*both(renderer, oracle, s, rays), min_hits=3000)
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 9, 33])
+def test_tiny_scenes(renderer, oracle, n):
+    s, p = soup(n, 100 + n, size=0.8)
+    rays = np.concatenate([np.repeat(rays_at(p.mean(axis=1), n), 40, axis=0) + 0, random_rays(4000, n)])
+    assert_identical(*both(renderer, oracle, s, rays), min_hits=n)
+
+
+def test_empty_scene_renders_background(renderer):
+    mat = make_material(base_color=(0.5, 0.5, 0.5))
+    s = _assemble([[]], [mat])
+    assert s.n_faces == 0
+    renderer.set_scene(s)
+    renderer.build_accel()
+    ids, _ = renderer.trace_closest(random_rays(1000, 1))
+    assert (ids == MISS).all()
+    W, H = 32, 16
+    renderer.set_resolution(W, H)
+    layers = DeviceLayers(W, H)
+    c = scenes.CORNELL_CAMERA
+    cam = Camera(api.camera_walk(c["origin"], 0.0, 0.0, 0, 0.0), c["fov"], c["F"], c["focus"])
+    renderer.render(cam, (0.25, 0.5, 0.75), layers, 2, 4)
+    renderer.wait()
+    img = layers.download("beauty")[..., :3]
+    assert np.allclose(img, (0.25, 0.5, 0.75), atol=1e-6)
+    assert (layers.download("depth") == 0).all()
+
+
+def test_exact_ties_take_the_lowest_face(renderer, oracle):
+    """Coincident triangles give exactly equal t: the lower global face index wins on both sides
+    (the tie rule DESIGN.md states; OptiX leaves it unspecified)."""
+    base, p = soup(200, 21)
+    tris = [(tri, 0) for tri in p]
+    dup = [tris[i] for i in (5, 5, 17, 60, 60, 60, 199)]
+    mat = make_material(base_color=(0.7, 0.7, 0.7))
+    s = _assemble([tris + dup, dup], [mat])        # duplicates inside the sub-mesh and in a second one
+    rays = np.concatenate([np.repeat(rays_at(p.mean(axis=1), 3), 8, axis=0), random_rays(20000, 4)])
+    ids_g, tuv_g, ids_o, tuv_o = both(renderer, oracle, s, rays)
+    assert_identical(ids_g, tuv_g, ids_o, tuv_o, min_hits=500)
+    hit = ids_o[:, 0] != MISS
+    assert (ids_g[hit, 0] == 0).all() and (ids_g[hit, 1] < 200).all()   # never a duplicate
+
+
+def test_degenerate_triangles_are_never_hit(renderer, oracle):
+    s0, p = soup(300, 31)
+    q = p.copy()
+    q[::3, 2] = q[::3, 1]                      # zero area: two equal vertices
+    q[1::7, 1] = (q[1::7, 0] + q[1::7, 2]) / 2  # zero area: collinear
+    mat = make_material(base_color=(0.7, 0.7, 0.7))
+    s = _assemble([[(tri, 0) for tri in q]], [mat])
+    rays = np.concatenate([rays_at(p.mean(axis=1), 8), random_rays(20000, 9)])
+    ids_g, tuv_g, ids_o, tuv_o = both(renderer, oracle, s, rays)
+    assert_identical(ids_g, tuv_g, ids_o, tuv_o, min_hits=100)
+    hit = ids_g[:, 0] != MISS
+    dead = np.zeros(300, bool)
+    dead[::3] = True
+    assert not dead[ids_g[hit, 1]].any()
+
+
+def test_instance_transforms(renderer, oracle):
+    """Sub-mesh i is instance i with transform i (renderer.h:509-527): rotation, non-uniform scale and
+    translation; ids are (instance, primitive-in-sub-mesh)."""
+    mat = make_material(base_color=(0.7, 0.7, 0.7))
+    _, p = soup(150, 41, size=0.3)
+    shapes = [[(tri, 0) for tri in p[:50]], [(tri, 0) for tri in p[50:100]], [(tri, 0) for tri in p[100:]]]
+    s = _assemble(shapes, [mat])
+    def trs(angle, scale, t):
+        c, sn = np.cos(angle), np.sin(angle)
+        R = np.array([[c, 0, sn], [0, 1, 0], [-sn, 0, c]], np.float32) @ np.diag(scale).astype(np.float32)
+        M = np.eye(4, dtype=np.float32)
+        M[:3, :3] = R
+        M[:3, 3] = t
+        return M.T.reshape(16)              # column-major mat4
+    s.transforms = np.stack([trs(0.0, (1, 1, 1), (0, 0, 0)), trs(0.7, (1.5, 0.5, 2.0), (3, -1, 0.5)),
+                             trs(-2.1, (0.3, 2.0, 1.0), (-4, 2, 1))]).astype(np.float32)
+    s.instance_ids = np.repeat(np.arange(3, dtype=np.uint32), 50)
+    rays = random_rays(80000, 42, -7, 7)
+    ids_g, tuv_g, ids_o, tuv_o = both(renderer, oracle, s, rays)
+    assert_identical(ids_g, tuv_g, ids_o, tuv_o, min_hits=300)
+    hit = ids_g[:, 0] != MISS
+    assert set(np.unique(ids_g[hit, 0])) == {0, 1, 2} and ids_g[hit, 1].max() < 50
+
+
+def test_alpha_cutout_matches_oracle(renderer, oracle):
+    """Any-hit programs (pt.cu:545-678): texels with alpha < 0.5 in the base-colour map are holes for
+    radiance, shadow and light rays alike -- first-hit depth and the image against the reference."""
+    tex = np.zeros((16, 16, 4), np.uint8)
+    tex[..., :3] = 200
+    yy, xx = np.mgrid[0:16, 0:16]
+    tex[..., 3] = np.where((xx // 4 + yy // 4) % 2 == 0, 255, 0)      # checkerboard of holes
+    front = make_material(base_color=(0.8, 0.8, 0.8), base_color_texture_id=0)
+    back = make_material(base_color=(0.2, 0.6, 0.9))
+    wall = [(t, 0) for t in _quad((-1, 0, 0), (1, 0, 0), (1, 2, 0), (-1, 2, 0))]
+    behind = [(t, 1) for t in _quad((-2, -1, -1), (2, -1, -1), (2, 3, -1), (-2, 3, -1))]
+    s = _assemble([wall, behind], [front, back])
+    s.textures = [(tex, True)]
+    W, H = 64, 64
+    c = dict(scenes.CORNELL_CAMERA)
+    cam = Camera(api.camera_walk(c["origin"], 0.0, 0.0, 0, 0.0), c["fov"], c["F"], c["focus"])
+    renderer.set_scene(s)
+    renderer.build_accel()
+    renderer.set_resolution(W, H)
+    layers = DeviceLayers(W, H)
+    renderer.render(cam, (1, 1, 1), layers, 4, 4)
+    renderer.wait()
+    oracle.set_scene(s)
+    oracle.build_accel()
+    oracle.set_resolution(W, H)
+    ref, _ = oracle.render_canonical(cam, (1, 1, 1), 4, 4, n_threads=os.cpu_count() or 1)
+    d_g, d_o = layers.download("depth").reshape(H, W), ref["depth"].reshape(H, W)
+    assert np.isclose(d_g, d_o, rtol=1e-5, atol=1e-6).mean() >= 0.999
+    assert d_g.max() > d_g[d_g > 0].min() * 1.15           # both the wall and the quad behind it are seen
+    from conftest import rel_mse
+    assert rel_mse(layers.download("beauty")[..., :3], ref["beauty"][..., :3]) < 1e-3
