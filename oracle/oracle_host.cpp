@@ -53,7 +53,13 @@ using std::isnan;
 
 #include <optix.h>  // oracle/shim/optix.h
 
-// the reference integrator, verbatim (build-dir copy with the pt.cu:181 patch)
+// Device semantics of clamp(x, 0.0f, 1.0f): nvcc lowers the reference's fmaxf(0, fminf(x, 1)) to the
+// .sat modifier, which maps NaN to 0 (the host expression maps NaN to 1).  Used by the patched copies
+// of pt.cu:375 (regularize_weight) and pt.cu:460 (roulette probability); see oracle/Makefile.
+static inline float orc_sat(float x) { return x != x ? 0.0f : fmaxf(0.0f, fminf(x, 1.0f)); }
+static inline float3 orc_sat3(const float3& v) { return make_float3(orc_sat(v.x), orc_sat(v.y), orc_sat(v.z)); }
+
+// the reference integrator, verbatim (build-dir copy with the patches listed in oracle/Makefile)
 #include "patched/pt.cu"
 
 // glm only for glm::inverse, to mirror renderer.h:404-421 bit-for-bit
