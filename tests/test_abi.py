@@ -67,12 +67,15 @@ def test_no_cpu_fallback():
 
 def test_product_does_not_import_oracle():
     """oracle/ is test infrastructure: nothing in the package or the C++ sources refers to it."""
-    pkg = os.path.join(ROOT, "fredholm_b200")
-    for dirpath, _, files in os.walk(pkg):
-        if "build" in dirpath.split(os.sep):
-            continue
-        for f in files:
-            if f.endswith((".py", ".cpp", ".cu", ".h", ".cuh")):
-                text = open(os.path.join(dirpath, f), errors="replace").read()
-                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
-                assert "libfredholm_oracle" not in text, f
+    sources = []
+    for top in ("fredholm_b200", "tools", "examples", "include"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, top)):
+            if any(d.startswith("build") for d in dirpath.split(os.sep)):
+                continue
+            sources += [os.path.join(dirpath, f) for f in files
+                        if f.endswith((".py", ".cpp", ".cu", ".h", ".cuh", ".sh"))]
+    assert len(sources) > 30
+    for path in sources:
+        text = open(path, errors="replace").read()
+        assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), path
+        assert "libfredholm_oracle" not in text, path

@@ -1,5 +1,5 @@
 """CUDA path vs the committed golden vectors (outputs of the reference's own integrator
-sources, tools/gen_golden.py).  Runs on the GPU box without /root/reference; everything goes
+sources, tests/tools/gen_golden.py).  Runs on the GPU box without /root/reference; everything goes
 through the C ABI (fredholm_b200.api -> libfredholm_b200.so)."""
 import os
 import sys

@@ -1,6 +1,6 @@
 """CPU tests of the ORACLE (test infrastructure): the reference's own integrator sources
 compiled for the host (oracle/Makefile -> oracle/_ref/libfredholm_oracle.so) must reproduce
-the committed golden vectors (tools/gen_golden.py), and the parts the oracle has to restate
+the committed golden vectors (tests/tools/gen_golden.py), and the parts the oracle has to restate
 itself -- traversal -- are pinned against a brute-force loop over all triangles.
 
 The reference has no tests or known-answer vectors of its own."""

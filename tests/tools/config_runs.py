@@ -1,5 +1,5 @@
 """Measured runs of BASELINE.json's five configurations on one B200.
-Prints one JSON object per configuration; `python tools/config_runs.py [c1 c2 c3 c4 c5] > profiles/...`.
+Prints one JSON object per configuration; `python tests/tools/config_runs.py [c1 c2 c3 c4 c5] > profiles/...`.
 
   C1  Cornell box 256x256, 16 spp, depth 8: throughput + relMSE vs the reference integrator (oracle, whole image)
       + the oracle's single-thread rate (the reported CPU baseline of 8(d)).
@@ -19,7 +19,7 @@ import time
 
 import numpy as np
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from fredholm_b200 import Camera, DeviceLayers, Renderer, api, scenes  # noqa: E402
 from oracle import binding as ob  # noqa: E402  (checker only)
 

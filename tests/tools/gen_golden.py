@@ -7,14 +7,14 @@ fixtures are "outputs of the reference itself run here": they pin both the oracl
 (tests/test_oracle_golden.py, CPU) and the CUDA path (tests/test_gpu_golden.py, GPU box,
 where /root/reference does not exist).
 
-    python tools/gen_golden.py          # needs /root/reference (builds oracle/_ref)
+    python tests/tools/gen_golden.py          # needs /root/reference (builds oracle/_ref)
 """
 import os
 import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
