@@ -37,7 +37,7 @@ def _slice_sums(o, cam, first, n):
 
 def _worker(rank, world, port, out_path):
     sys.path.insert(0, ROOT)
-    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    sys.path.insert(0, os.path.join(ROOT, "tests", "tools"))
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     import torch.distributed as dist
@@ -60,7 +60,7 @@ def _worker(rank, world, port, out_path):
 @pytest.mark.timeout(300)
 def test_two_rank_sample_sharding(oracle_mod, tmp_path):
     import torch.multiprocessing as mp
-    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    sys.path.insert(0, os.path.join(ROOT, "tests", "tools"))
     import gen_golden as gg
     from fredholm_b200 import scenes
     out = str(tmp_path / "img.npy")

@@ -14,7 +14,7 @@ import pytest
 from conftest import ROOT, golden, rel_mse
 from fredholm_b200 import Camera, scenes
 
-sys.path.insert(0, os.path.join(ROOT, "tools"))
+sys.path.insert(0, os.path.join(ROOT, "tests", "tools"))
 import gen_golden as gg  # noqa: E402
 
 
