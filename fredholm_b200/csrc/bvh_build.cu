@@ -565,7 +565,7 @@ bool builder_is_ploc()
 int ploc_radius()
 {
   const char* e = getenv("FRD_PLOC_RADIUS");
-  const int r = e ? atoi(e) : 16;
+  const int r = e ? atoi(e) : 8;
   return r < 1 ? 1 : (r > kPlocMaxRadius ? kPlocMaxRadius : r);
 }
 
