@@ -223,3 +223,56 @@ def test_back_face_of_an_opaque_surface(renderer, oracle):
     assert np.allclose(got[~hit], 1.0)
     st, rc = renderer.statistics(), oracle.ray_counts()
     assert st["rays_radiance"] == rc["rays_radiance"]
+
+
+@pytest.mark.parametrize("F,focus", [(100.0, 10000.0), (1.4, 3.0), (0.8, 1.2)])
+def test_thin_lens_rays_match_reference(renderer, oracle, F, focus):
+    """sample_ray_thinlens_camera (camera.cu:24-53) with a wide-open lens: lens radius 2f/F, concentric
+    disk sample, focus plane -- origins and directions of every pixel's first sample, and the image
+    with depth of field."""
+    s = scenes.cornell_box()
+    c = scenes.CORNELL_CAMERA
+    cam = Camera(api.camera_walk(c["origin"], 40.0, 30.0, 0, 0.0), c["fov"], F, focus)
+    W, H = 64, 48
+    for x in (renderer, oracle):
+        x.set_scene(s)
+        x.build_accel()
+        x.set_resolution(W, H)
+    for n_spp in (0, 5, 21):
+        a, b = renderer.primary_rays(cam, n_spp), oracle.primary_rays(cam, n_spp)
+        assert np.allclose(a, b, rtol=1e-5, atol=1e-5)
+    if F < 100.0:
+        o = renderer.primary_rays(cam, 0).reshape(-1, 6)[:, :3]
+        assert np.ptp(o, axis=0).max() > 1e-2          # the lens really has an aperture
+    layers = DeviceLayers(W, H)
+    renderer.render(cam, (0, 0, 0), layers, 8, 5)
+    renderer.wait()
+    ref, _ = oracle.render_canonical(cam, (0, 0, 0), 8, 5, n_threads=os.cpu_count() or 1)
+    from conftest import rel_mse
+    assert rel_mse(layers.download("beauty")[..., :3], ref["beauty"][..., :3]) < 1e-3
+
+
+def test_emitter_seen_from_behind(renderer, oracle):
+    """has_emission / __closesthit__light (pt.cu:125-139, 952-998): an emissive quad facing away from
+    the camera above a floor -- what the back of an emitter shows and what it gives to next-event
+    estimation and MIS rays, against the reference."""
+    lamp = make_material(base_color=(0.5, 0.5, 0.5), specular_color=(0, 0, 0), emission=1.0, emission_color=(9, 8, 7))
+    floor = make_material(base_color=(0.7, 0.7, 0.7))
+    panel = _quad((-0.6, 0.4, 0.0), (-0.6, 1.6, 0.0), (0.6, 1.6, 0.0), (0.6, 0.4, 0.0))     # normal -z: away
+    ground = _quad((-2, 0, 2), (2, 0, 2), (2, 0, -2), (-2, 0, -2))
+    s = _assemble([[(t, 0) for t in panel], [(t, 1) for t in ground]], [lamp, floor])
+    c = scenes.CORNELL_CAMERA
+    cam = Camera(api.camera_walk(c["origin"], 0.0, 60.0, 0, 0.0), c["fov"], c["F"], c["focus"])
+    W, H = 64, 64
+    for x in (renderer, oracle):
+        x.set_scene(s)
+        x.build_accel()
+        x.set_resolution(W, H)
+    layers = DeviceLayers(W, H)
+    renderer.render(cam, (0.05, 0.05, 0.05), layers, 16, 4)
+    renderer.wait()
+    ref, _ = oracle.render_canonical(cam, (0.05, 0.05, 0.05), 16, 4, n_threads=os.cpu_count() or 1)
+    got, want = layers.download("beauty")[..., :3], ref["beauty"][..., :3]
+    from conftest import rel_mse
+    assert np.isfinite(got).all() and rel_mse(got, want) < 1e-3
+    assert abs(got.mean() - want.mean()) < 0.01 * want.mean()
