@@ -58,7 +58,9 @@ struct ClosestPolicy {
   FR_D void load(uint32_t item, float3& o, float3& d, float& tmin, float& tmax)
   {
     slot = q[item];
-    const float4 ro = wb.ray_o[slot], rd = wb.ray_d[slot];
+    // path state and ray records are read once per bounce: streaming loads / stores (evict-first)
+    // leave the L2 to the tree (-1.2 % any-hit time)
+    const float4 ro = __ldcs(&wb.ray_o[slot]), rd = __ldcs(&wb.ray_d[slot]);
     o = f3(ro);
     d = f3(rd);
     tmin = 0.0f;
@@ -68,7 +70,7 @@ struct ClosestPolicy {
   {
     int cls = -1;
     if (has) {
-      wb.hit[slot] = make_float4(h.t, h.u, h.v, __uint_as_float(h.face));
+      __stcs(&wb.hit[slot], make_float4(h.t, h.u, h.v, __uint_as_float(h.face)));
       // a miss only needs work for camera rays (sky seen directly, pt.cu:504-523)
       cls = h.face != kNoHit ? (int)sc.face_class[h.face] : (depth == 0 ? (int)CLS_MISS : -1);
     }
@@ -107,7 +109,7 @@ struct ShadowPolicy {
   FR_D void load(uint32_t item, float3& o, float3& d, float& tmin, float& tmax)
   {
     if (order) item = order[item];
-    const float4 r0 = q[3ull * item], r1 = q[3ull * item + 1], r2 = q[3ull * item + 2];
+    const float4 r0 = __ldcs(q + 3ull * item), r1 = __ldcs(q + 3ull * item + 1), r2 = __ldcs(q + 3ull * item + 2);
     o = f3(r0);
     d = f3(r1);
     tmin = 0.0f;
@@ -152,7 +154,7 @@ struct LightPolicy {
   FR_D void load(uint32_t item, float3& ro, float3& rd, float& tmin, float& tmax)
   {
     if (order) item = order[item];
-    const float4 r0 = q[3ull * item], r1 = q[3ull * item + 1], r2 = q[3ull * item + 2];
+    const float4 r0 = __ldcs(q + 3ull * item), r1 = __ldcs(q + 3ull * item + 1), r2 = __ldcs(q + 3ull * item + 2);
     ro = o = f3(r0);
     rd = d = f3(r1);
     tmin = 0.0f;
