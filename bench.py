@@ -354,18 +354,18 @@ def run_ours(args):
     ms_top, n_top = stages[top]
     achieved = (per_rank * bytes_per_unit / 1e9) / (ms_top / 1e3) if ms_top > 0 else 0.0
     # DRAM bytes per ray of that kernel from the committed `ncu --set full` capture
-    # (profiles/r1i_kernels_ncu_full.txt: dram__bytes_read.sum + dram__bytes_write.sum over the rays of
+    # (profiles/r1k_kernels_ncu_full.txt: dram__bytes_read.sum + dram__bytes_write.sum over the rays of
     # the captured launches -- 33.18 M primary rays; <= 3 x 18.2 M depth-0 visibility rays), scaled to the
     # rays of one launch here
-    ncu_dram_bytes_per_unit = {"trace_closest": 68.1, "trace_shadow": 99.0}.get(top)
-    ncu_issue = {"trace_closest": (66.5, 20.8), "trace_shadow": (72.1, 19.1)}.get(top, (None, None))
+    ncu_dram_bytes_per_unit = {"trace_closest": 68.0, "trace_shadow": 99.0}.get(top)
+    ncu_issue = {"trace_closest": (70.4, 20.7), "trace_shadow": (72.9, 19.0)}.get(top, (None, None))
     units_per_launch = per_rank / max(n_top, 1)
     traffic = ncu_dram_bytes_per_unit * units_per_launch if ncu_dram_bytes_per_unit else None
     roofline = {"kernel": "k_" + top, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "traffic_source": "ncu --set full capture (profiles/), DRAM bytes per ray x rays per launch",
                 "sm_issue": {"issue_slots_busy_pct": ncu_issue[0], "active_lanes_per_instruction": ncu_issue[1],
-                             "source": "profiles/r1i_kernels_ncu_full.txt (ncu --set full of the depth-0 launches, 16 spp)"},
+                             "source": "profiles/r1k_kernels_ncu_full.txt (ncu --set full of the depth-0 launches, 16 spp)"},
                 "launches": n_top, "avg_launch_ms": ms_top / max(n_top, 1),
                 "units_per_launch": units_per_launch, "algorithmic_bytes_per_unit": bytes_per_unit,
                 "note": "traversal is SM-issue / latency bound, not HBM bound (SURVEY.md 8(d)); issue-slot "
