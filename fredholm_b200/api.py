@@ -101,6 +101,7 @@ SIGNATURES = {
     "fr_get_sample_count": (C.c_uint32, [_vp]),
     "fr_set_film_mode": (C.c_int, [_vp, C.c_int]),
     "fr_set_max_wave_paths": (C.c_int, [_vp, C.c_uint64]),
+    "fr_set_single_launch": (C.c_int, [_vp, C.c_int]),
     "fr_render": (C.c_int, [_vp, _fp, C.c_float, C.c_float, C.c_float, _fp, C.POINTER(_Layers), C.c_uint32,
                             C.c_uint32]),
     "fr_wait": (C.c_int, [_vp]),
@@ -480,6 +481,10 @@ class Renderer:
 
     def set_max_wave_paths(self, n):
         _check(lib().fr_set_max_wave_paths(self._h, int(n)))
+
+    def set_single_launch(self, on):
+        """render(n_samples) as ONE reference launch (payload.firsthit outlives the sample loop, pt.cu:432-433)."""
+        _check(lib().fr_set_single_launch(self._h, 1 if on else 0))
 
     # ---- render ----
     def render(self, camera: Camera, bg_color, layers, n_samples, max_depth):

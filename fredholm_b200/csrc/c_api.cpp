@@ -357,6 +357,10 @@ int fr_set_max_wave_paths(fr_renderer* r, uint64_t n_paths)
 {
   return guarded([&] { r->renderer.set_max_wave_paths((size_t)n_paths); });
 }
+int fr_set_single_launch(fr_renderer* r, int on)
+{
+  return guarded([&] { r->renderer.set_single_launch(on != 0); });
+}
 
 int fr_render(fr_renderer* r, const float* camera_transform12, float fov, float F, float focus, const float* bg,
               const fr_layers* layers_dev, uint32_t n_samples, uint32_t max_depth)

@@ -151,6 +151,21 @@ void Integrator::render(const SceneView& scene, const fredholm::CameraParams& ca
   for (int c = 0; c < CLS_COUNT; ++c) wb.class_queue[c] = m_class_queue[c].get();
   wb.light = m_light.get();
   wb.ctl = m_ctl.get();
+  wb.first_hit = nullptr;
+  wb.pix_aov0 = wb.pix_aov1 = wb.pix_aov2 = nullptr;
+  if (m_single_launch) {
+    const size_t n_pixels = (size_t)width * height;
+    m_first_hit.reserve(n_pixels);
+    FR_CUDA_CHECK(cudaMemsetAsync(m_first_hit.get(), 0xff, n_pixels * sizeof(uint32_t), m_stream));
+    for (int k = 0; k < 3; ++k) {
+      m_pix_aov[k].reserve(n_pixels);
+      FR_CUDA_CHECK(cudaMemsetAsync(m_pix_aov[k].get(), 0, n_pixels * sizeof(float4), m_stream));
+    }
+    wb.first_hit = m_first_hit.get();
+    wb.pix_aov0 = m_pix_aov[0].get();
+    wb.pix_aov1 = m_pix_aov[1].get();
+    wb.pix_aov2 = m_pix_aov[2].get();
+  }
 
   for (uint32_t done = 0; done < n_samples; done += per_wave) {
     WaveParams wp;
@@ -160,6 +175,7 @@ void Integrator::render(const SceneView& scene, const fredholm::CameraParams& ca
     wp.max_depth = max_depth;
     wp.seed = seed;
     wp.want_aov = (layers.position || layers.normal || layers.depth || layers.texcoord || layers.albedo) ? 1u : 0u;
+    wp.single_launch = m_single_launch ? 1u : 0u;
     wp.camera = camera;
 
     stage(STAGE_ADVANCE, [&] { launch_wave_begin(m_stream, wb, (unsigned long long)wp.n_samples * width * height); });
@@ -174,7 +190,8 @@ void Integrator::render(const SceneView& scene, const fredholm::CameraParams& ca
       };
       if (depth > 0) sort_queue(1u, SORT_RADIANCE0 + (int)(depth & 1u), true);
       stage(STAGE_TRACE_CLOSEST, [&] { launch_trace_closest(m_stream, scene, wb, depth, order); });
-      if (depth == 0) stage(STAGE_SHADE, [&] { launch_miss(m_stream, scene, wb); });
+      if (depth == 0 && m_single_launch) stage(STAGE_SHADE, [&] { launch_first_hit(m_stream, wp, wb); });
+      if (depth == 0) stage(STAGE_SHADE, [&] { launch_miss(m_stream, wp, scene, wb); });
       for (int c = 0; c < CLS_MISS; ++c)
         if (class_mask & (1u << c)) stage(STAGE_SHADE, [&] { launch_shade(m_stream, wp, scene, wb, depth, c); });
       if (scene.has_dir_light) {

@@ -43,6 +43,10 @@ class Integrator
 
   // paths kept in flight per wave; rounded down to whole samples (at least one)
   void set_max_wave_paths(size_t n) { m_max_wave_paths = n; }
+  // single-launch mode: one render() call behaves like ONE reference launch of n_samples (payload.firsthit and
+  // the first-hit AOVs outlive the sample loop, pt.cu:432-433, 744-759); default off = one launch per sample
+  void set_single_launch(bool on) { m_single_launch = on; }
+  bool single_launch() const { return m_single_launch; }
   size_t max_wave_paths() const { return m_max_wave_paths; }
 
   // Renders samples [sample_base, sample_base + n_samples) of every pixel into
@@ -92,6 +96,9 @@ class Integrator
   void stage(int id, F&& launch);
 
   DevBuf<float4> m_ray_o, m_ray_d, m_hit, m_thr, m_L, m_aov0, m_aov1, m_aov2;
+  bool m_single_launch = false;
+  DevBuf<uint32_t> m_first_hit;           // [n_pixels], single-launch mode only
+  DevBuf<float4> m_pix_aov[3];            // [n_pixels] each
   DevBuf<uint32_t> m_queue[2];
   DevBuf<uint32_t> m_class_queue[CLS_COUNT];
   DevBuf<ShadowRay> m_shadow[3];

@@ -464,6 +464,7 @@ void Renderer::scale_layers(const RenderLayer& render_layer, float scale)
   m_impl->integrator->scale_layers(render_layer, m_impl->width * m_impl->height, scale);
 }
 void Renderer::set_max_wave_paths(size_t n_paths) { m_impl->integrator->set_max_wave_paths(n_paths); }
+void Renderer::set_single_launch(bool on) { m_impl->integrator->set_single_launch(on); }
 
 void Renderer::set_stage_timing(bool on) { m_impl->integrator->set_stage_timing(on); }
 void Renderer::get_stage_times(double ms[kStageCount], unsigned long long launches[kStageCount])

@@ -54,6 +54,7 @@ __global__ void __launch_bounds__(kBlock) k_generate(WaveParams wp, WaveBuffers 
     uint32_t x, y;
     const bool inside = slot_to_pixel(wp.film, slot % wp.film.slots_per_sample, x, y);
     wb.L[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (wp.single_launch) wb.hit[slot] = make_float4(0.f, 0.f, 0.f, __uint_as_float(kNoHit));  // read by k_first_hit
     if (wp.want_aov) {  // the first-hit words are only kept when a layer will read them
       wb.aov0[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
       wb.aov1[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -146,12 +147,18 @@ FR_D void add_radiance(const WaveBuffers& wb, uint32_t slot, const float3& v)
 }
 
 // camera rays that left the scene: __miss__radiance with firsthit (pt.cu:504-523)
-__global__ void __launch_bounds__(kBlock) k_miss(SceneView sc, WaveBuffers wb)
+__global__ void __launch_bounds__(kBlock) k_miss(WaveParams wp, SceneView sc, WaveBuffers wb)
 {
   WaveControl* ctl = wb.ctl;
   const uint32_t n = ctl->n_class[CLS_MISS];
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const uint32_t slot = wb.class_queue[CLS_MISS][i];
+    if (wp.single_launch) {
+      // firsthit is already false once an earlier sample of the launch hit geometry (pt.cu:509)
+      uint32_t px, py;
+      slot_to_pixel(wp.film, slot % wp.film.slots_per_sample, px, py);
+      if (wp.sample_base + slot / wp.film.slots_per_sample > wb.first_hit[px + wp.film.width * py]) continue;
+    }
     const float3 d = f3(wb.ray_d[slot]);
     const float3 thr = f3(wb.thr[slot]);
     add_radiance(wb, slot, thr * sky_radiance(sc, d));
@@ -238,9 +245,18 @@ __global__ void __launch_bounds__(kBlock, FRD_SHADE_BLOCKS) k_shade(WaveParams w
         }
       }
 
-      if (depth == 0) {
+      // single-launch mode: only the first sample of the launch that hits geometry still has
+      // payload.firsthit (pt.cu:744-759); later ones shade a directly visible emitter like any surface
+      const uint32_t pixel = px + wp.film.width * py;
+      const bool first_hit = depth == 0 && (!wp.single_launch || wb.first_hit[pixel] == smp.n_spp);
+      if (first_hit && wp.single_launch) {
+        wb.pix_aov0[pixel] = make_float4(x.x, x.y, x.z, hit.x);
+        wb.pix_aov1[pixel] = make_float4(fr.n.x, fr.n.y, fr.n.z, uv.x);
+        wb.pix_aov2[pixel] = make_float4(sp.base_color.x, sp.base_color.y, sp.base_color.z, uv.y);
+      }
+      if (first_hit) {
         // first-hit AOVs and directly visible emitters (pt.cu:745-760)
-        if (wp.want_aov) {
+        if (wp.want_aov && !wp.single_launch) {
           wb.aov0[slot] = make_float4(x.x, x.y, x.z, hit.x);
           wb.aov1[slot] = make_float4(fr.n.x, fr.n.y, fr.n.z, uv.x);
           wb.aov2[slot] = make_float4(sp.base_color.x, sp.base_color.y, sp.base_color.z, uv.y);
@@ -411,6 +427,23 @@ __global__ void k_wave_begin(WaveControl* ctl, unsigned long long n_paths)
   }
 }
 
+// ---- single-launch mode: which sample of the launch consumed payload.firsthit ------------
+__global__ void __launch_bounds__(256) k_first_hit(WaveParams wp, WaveBuffers wb)
+{
+  const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= wp.film.width || y >= wp.film.height) return;
+  const uint32_t pixel = x + wp.film.width * y;
+  if (wb.first_hit[pixel] != 0xffffffffu) return;  // an earlier wave of this launch
+  const uint32_t slot0 = pixel_to_slot(wp.film, x, y);
+  for (uint32_t s = 0; s < wp.n_samples; ++s) {
+    if (__float_as_uint(wb.hit[s * wp.film.slots_per_sample + slot0].w) != kNoHit) {
+      wb.first_hit[pixel] = wp.sample_base + s;
+      return;
+    }
+  }
+}
+
 // ---- film -----------------------------------------------------------------------------
 // Streaming mean of the reference (pt.cu:480-501), applied sample by sample in sample
 // order so that the result is independent of how many samples one wave carries.
@@ -440,7 +473,12 @@ __global__ void __launch_bounds__(256) k_film(WaveParams wp, WaveBuffers wb, fre
     float3 radiance = f3(L);
     if (bad3(radiance)) radiance = f3(0.f);  // pt.cu:475-478
     float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0;
-    if (wp.want_aov) a0 = wb.aov0[slot], a1 = wb.aov1[slot], a2 = wb.aov2[slot];
+    if (wp.single_launch) {
+      // the payload keeps the first hit's values for every later sample of the launch (pt.cu:482-487)
+      if (n_spp >= wb.first_hit[pixel]) a0 = wb.pix_aov0[pixel], a1 = wb.pix_aov1[pixel], a2 = wb.pix_aov2[pixel];
+    } else if (wp.want_aov) {
+      a0 = wb.aov0[slot], a1 = wb.aov1[slot], a2 = wb.aov2[slot];
+    }
     if (film_mode == FILM_MEAN) {
       const float nf = (float)n_spp;
       const float coef = 1.0f / (nf + 1.0f);
@@ -652,11 +690,19 @@ void launch_shade(cudaStream_t s, const WaveParams& wp, const SceneView& sc, con
   }
 }
 
-void launch_miss(cudaStream_t s, const SceneView& sc, const WaveBuffers& wb)
+void launch_first_hit(cudaStream_t s, const WaveParams& wp, const WaveBuffers& wb)
+{
+  const dim3 block(32, 8);
+  const dim3 grid((wp.film.width + 31) / 32, (wp.film.height + 7) / 8);
+  k_first_hit<<<grid, block, 0, s>>>(wp, wb);
+  FR_CUDA_LAUNCH_CHECK();
+}
+
+void launch_miss(cudaStream_t s, const WaveParams& wp, const SceneView& sc, const WaveBuffers& wb)
 {
   static int grid = 0;
   if (grid == 0) grid = persistent_grid(reinterpret_cast<const void*>(k_miss), kBlock);
-  k_miss<<<grid, kBlock, 0, s>>>(sc, wb);
+  k_miss<<<grid, kBlock, 0, s>>>(wp, sc, wb);
   FR_CUDA_LAUNCH_CHECK();
 }
 

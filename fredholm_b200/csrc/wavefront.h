@@ -119,6 +119,11 @@ struct WaveBuffers {
   ShadowRay* shadow[3];     // [n_slots] directional / sky / area-light NEE rays
   LightRay* light;          // [n_slots] MIS rays
   WaveControl* ctl;
+  // single-launch mode (reference quirk: RadiancePayload outlives the sample loop, pt.cu:432-433)
+  uint32_t* first_hit;  // [n_pixels] index of the first sample of this launch whose camera ray hit geometry
+  float4* pix_aov0;     // [n_pixels] that sample's first-hit words (position|depth, normal|u, albedo|v)
+  float4* pix_aov1;
+  float4* pix_aov2;
 };
 
 // image <-> path slot mapping: pixels are walked in 8x4 tiles so that one warp owns
@@ -168,6 +173,7 @@ struct WaveParams {
   uint32_t max_depth;
   uint32_t seed;
   uint32_t want_aov;     // any first-hit layer (position / normal / depth / texcoord / albedo) is bound
+  uint32_t single_launch;  // 1: all samples of this render() call share one payload like ONE reference launch
   fredholm::CameraParams camera;
 };
 

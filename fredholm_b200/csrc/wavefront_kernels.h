@@ -17,7 +17,8 @@ void launch_wave_begin(cudaStream_t s, const WaveBuffers& wb, unsigned long long
 void launch_generate(cudaStream_t s, const WaveParams& wp, const WaveBuffers& wb);
 void launch_shade(cudaStream_t s, const WaveParams& wp, const SceneView& sc, const WaveBuffers& wb, uint32_t depth,
                   int cls);
-void launch_miss(cudaStream_t s, const SceneView& sc, const WaveBuffers& wb);
+void launch_miss(cudaStream_t s, const WaveParams& wp, const SceneView& sc, const WaveBuffers& wb);
+void launch_first_hit(cudaStream_t s, const WaveParams& wp, const WaveBuffers& wb);
 void launch_advance(cudaStream_t s, const WaveBuffers& wb);
 void launch_film(cudaStream_t s, const WaveParams& wp, const WaveBuffers& wb, const fredholm::RenderLayer& layers,
                  int film_mode);

@@ -103,6 +103,10 @@ class Renderer
   void set_film_mode(FilmMode mode);
   void scale_layers(const RenderLayer& render_layer, float scale);
   void set_max_wave_paths(size_t n_paths);
+  // One render(n_samples) call behaves like ONE reference launch of n_samples: payload.firsthit and the
+  // first-hit AOVs outlive the sample loop (pt.cu:432-433, 744-759) -- what app/rtcamp8.cpp produces.  Off by
+  // default: render(n_samples) equals n_samples launches of one sample, what the reference GUI produces.
+  void set_single_launch(bool on);
   // per-stage device time, measured with CUDA events on the renderer's stream;
   // stages: generate, trace_closest, shade, trace_shadow, trace_light, advance, film
   static constexpr int kStageCount = 7;
