@@ -35,21 +35,28 @@ def ours(renderer, cam, bg, spp, depth, wave=None):
     return out
 
 
-@pytest.mark.parametrize("scene_name", ["cornell", "standard"])
+@pytest.mark.parametrize("scene_name", ["cornell", "standard", "soup"])
 def test_one_launch_of_n_samples_matches_reference(renderer, oracle, scene_name):
     spp, depth = 8, 5
     if scene_name == "cornell":
         s, cam, bg = scenes.cornell_box(), cornell_camera(), (0.3, 0.4, 0.5)
+    elif scene_name == "soup":
+        # loose triangles in front of a bright constant background: silhouettes everywhere, so samples
+        # that miss after an earlier sample of the pixel hit (no sky for them, pt.cu:509) are common
+        from test_gpu_accel_edges import soup
+        s, cam, bg = soup(400, 77, size=0.35)[0], cornell_camera(), (0.9, 0.7, 0.5)
     else:
         s = scenes.standard_surface_scene(48, 24, sphere_res=(12, 6))
         c = scenes.STANDARD_CAMERA
-        cam, bg = Camera(api.camera_walk(c["origin"], 0.0, 150.0, 0, 0.0), c["fov"], c["F"], c["focus"]), (0, 0, 0)
+        cam, bg = Camera(api.camera_walk(c["origin"], 0.0, 30.0, 0, 0.0), c["fov"], c["F"], c["focus"]), (0, 0, 0)   # horizon in view
     for x in (renderer, oracle):
         x.set_scene(s)
         x.build_accel()
         x.set_resolution(W, H)
         if scene_name == "standard":
-            x.load_arhosek_sky(3.0, 0.3)
+            L = scenes.STANDARD_LIGHTING
+            x.set_directional_light(L["sun_le"], L["sun_dir"], L["sun_angle"])
+            x.load_arhosek_sky(L["turbidity"], L["albedo"])
     renderer.set_single_launch(True)
     got = ours(renderer, cam, bg, spp, depth)
     oracle.init_render_states()
@@ -64,7 +71,11 @@ def test_one_launch_of_n_samples_matches_reference(renderer, oracle, scene_name)
     # the quirk is visible: the canonical render of the same samples differs
     renderer.set_single_launch(False)
     canon = ours(renderer, cam, bg, spp, depth)
-    assert rel_mse(canon["beauty"][..., :3], ref["beauty"][..., :3]) > 1e-4
+    # (Cornell: the lamp is in view; standard scene: the frozen first-hit layers at every silhouette and
+    # wherever the depth varies inside a pixel)
+    if scene_name != "standard":
+        assert np.abs(canon["beauty"][..., :3] - got["beauty"][..., :3]).max() > 1e-2
+    assert (np.abs(canon["depth"] - got["depth"]) > 1e-4).sum() > 100
     # a launch split over several waves carries the per-pixel state along
     renderer.set_single_launch(True)
     split = ours(renderer, cam, bg, spp, depth, wave=2 * W * H)
