@@ -591,9 +591,15 @@ struct PhaseClock {
 };
 }  // namespace
 
-void build_bvh(cudaStream_t stream, const float3* d_vertices, const uint3* d_indices,
-               const uint32_t* d_face_submesh, const uint32_t* d_face_flags,
-               const fredholm::Matrix3x4* d_o2w, uint32_t n_faces, DeviceBvh& out)
+namespace
+{
+struct TreeTooDeep : std::runtime_error {
+  TreeTooDeep() : std::runtime_error("bvh: tree too deep for the traversal stack") {}
+};
+
+void build_bvh_with(bool use_ploc, cudaStream_t stream, const float3* d_vertices, const uint3* d_indices,
+                    const uint32_t* d_face_submesh, const uint32_t* d_face_flags,
+                    const fredholm::Matrix3x4* d_o2w, uint32_t n_faces, DeviceBvh& out)
 {
   out.n_faces = n_faces;
   out.depth = 1;
@@ -640,7 +646,7 @@ void build_bvh(cudaStream_t stream, const float3* d_vertices, const uint3* d_ind
   DevBuf<uint32_t> leaf_pos, order;
   const uint32_t* tri_order = sorted.get();
   out.ploc_rounds = 0;
-  if (builder_is_ploc() && n > 2) {
+  if (use_ploc && n > 2) {
     // ---- PLOC ----
     const int radius = ploc_radius();
     DevBuf<uint32_t> cl_a(n), cl_b(n), nearest(n), counters2(2);
@@ -728,8 +734,22 @@ void build_bvh(cudaStream_t stream, const float3* d_vertices, const uint3* d_ind
     out.bounds_hi[a] = hb[3 + a];
   }
   clk.mark("finish");
-  if (depth + 2 > (uint32_t)(kSmemStack + kLocalStack))
-    throw std::runtime_error("bvh: tree too deep for the traversal stack");
+  if (depth + 2 > (uint32_t)(kSmemStack + kLocalStack)) throw TreeTooDeep();
+}
+}  // namespace
+
+void build_bvh(cudaStream_t stream, const float3* d_vertices, const uint3* d_indices,
+               const uint32_t* d_face_submesh, const uint32_t* d_face_flags,
+               const fredholm::Matrix3x4* d_o2w, uint32_t n_faces, DeviceBvh& out)
+{
+  const bool ploc = builder_is_ploc();
+  try {
+    build_bvh_with(ploc, stream, d_vertices, d_indices, d_face_submesh, d_face_flags, d_o2w, n_faces, out);
+  } catch (const TreeTooDeep&) {
+    // an agglomerative tree has no depth bound; the radix tree's depth is bounded by the 63 key bits
+    if (!ploc) throw;
+    build_bvh_with(false, stream, d_vertices, d_indices, d_face_submesh, d_face_flags, d_o2w, n_faces, out);
+  }
 }
 
 }  // namespace frd
