@@ -323,13 +323,19 @@ struct ValidCluster {
 
 // Left-to-right position of the first triangle under `id`: walk to the root adding the sizes of
 // the left siblings passed on the way.  Gives every sub-tree a contiguous triangle range.
-__device__ __forceinline__ uint32_t ploc_first(const Lbvh& t, int n, uint32_t id)
+constexpr uint32_t kPlocMaxDepth = 2048;  // binary levels; deeper trees fall back to the radix tree
+
+__device__ __forceinline__ uint32_t ploc_first(const Lbvh& t, int n, uint32_t id, uint32_t* too_deep)
 {
   uint32_t first = 0;
   uint32_t cur = id;
-  for (;;) {
+  for (uint32_t steps = 0;; ++steps) {
     const uint32_t p = t.parent[cur];
     if (p == 0xffffffffu) break;
+    if (steps >= kPlocMaxDepth) {  // a degenerate chain: give up, the host rebuilds with the radix tree
+      *too_deep = 1u;
+      break;
+    }
     const uint2 ch = t.child[p];
     if (ch.y == cur) first += ch.x >= (uint32_t)(n - 1) ? 1u : t.visit[ch.x];
     cur = p;
@@ -338,11 +344,12 @@ __device__ __forceinline__ uint32_t ploc_first(const Lbvh& t, int n, uint32_t id
 }
 
 __global__ void k_ploc_ranges(int n, Lbvh t, const uint32_t* __restrict__ sorted, uint32_t* __restrict__ leaf_pos,
-                              uint32_t* __restrict__ order)
+                              uint32_t* __restrict__ order, uint32_t* __restrict__ too_deep)
 {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= 2 * n - 1) return;
-  const uint32_t first = ploc_first(t, n, (uint32_t)i);
+  const uint32_t first = ploc_first(t, n, (uint32_t)i, too_deep);
+  if (first >= (uint32_t)n) return;  // only possible after a depth bail-out
   if (i < n - 1) {
     t.range[i] = make_uint2(first, first + t.visit[i] - 1u);
   } else {
@@ -557,6 +564,10 @@ __global__ void k_empty_root(Node8* nodes)
   nodes[0] = out;
 }
 
+struct TreeTooDeep : std::runtime_error {
+  TreeTooDeep() : std::runtime_error("bvh: tree too deep for the traversal stack") {}
+};
+
 // builder selection (experiments / fallback): FRD_BVH_BUILDER=lbvh|ploc, FRD_PLOC_RADIUS=1..32
 bool builder_is_ploc()
 {
@@ -593,10 +604,6 @@ struct PhaseClock {
 
 namespace
 {
-struct TreeTooDeep : std::runtime_error {
-  TreeTooDeep() : std::runtime_error("bvh: tree too deep for the traversal stack") {}
-};
-
 void build_bvh_with(bool use_ploc, cudaStream_t stream, const float3* d_vertices, const uint3* d_indices,
                     const uint32_t* d_face_submesh, const uint32_t* d_face_flags,
                     const fredholm::Matrix3x4* d_o2w, uint32_t n_faces, DeviceBvh& out)
@@ -649,7 +656,7 @@ void build_bvh_with(bool use_ploc, cudaStream_t stream, const float3* d_vertices
   if (use_ploc && n > 2) {
     // ---- PLOC ----
     const int radius = ploc_radius();
-    DevBuf<uint32_t> cl_a(n), cl_b(n), nearest(n), counters2(2);
+    DevBuf<uint32_t> cl_a(n), cl_b(n), nearest(n), counters2(3);
     counters2.zero(stream);
     uint32_t* n_merged = counters2.get();
     uint32_t* n_selected = counters2.get() + 1;
@@ -682,8 +689,13 @@ void build_bvh_with(bool use_ploc, cudaStream_t stream, const float3* d_vertices
     FR_CUDA_CHECK(cudaMemcpyAsync(parent.get(), &none, sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
     leaf_pos.alloc(n);
     order.alloc(n);
-    k_ploc_ranges<<<(2 * n - 1 + B - 1) / B, B, 0, stream>>>(n, t, sorted.get(), leaf_pos.get(), order.get());
+    k_ploc_ranges<<<(2 * n - 1 + B - 1) / B, B, 0, stream>>>(n, t, sorted.get(), leaf_pos.get(), order.get(),
+                                                             counters2.get() + 2);
     FR_CUDA_LAUNCH_CHECK();
+    uint32_t too_deep = 0;
+    FR_CUDA_CHECK(cudaMemcpyAsync(&too_deep, counters2.get() + 2, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    FR_CUDA_CHECK(cudaStreamSynchronize(stream));
+    if (too_deep) throw TreeTooDeep();
     t.leaf_pos = leaf_pos.get();
     tri_order = order.get();
   } else {
@@ -735,6 +747,7 @@ void build_bvh_with(bool use_ploc, cudaStream_t stream, const float3* d_vertices
   }
   clk.mark("finish");
   if (depth + 2 > (uint32_t)(kSmemStack + kLocalStack)) throw TreeTooDeep();
+  if (use_ploc && getenv("FRD_PLOC_FORCE_FALLBACK")) throw TreeTooDeep();  // test hook for the fallback path
 }
 }  // namespace
 
@@ -748,6 +761,7 @@ void build_bvh(cudaStream_t stream, const float3* d_vertices, const uint3* d_ind
   } catch (const TreeTooDeep&) {
     // an agglomerative tree has no depth bound; the radix tree's depth is bounded by the 63 key bits
     if (!ploc) throw;
+    if (getenv("FRD_BVH_VERBOSE")) fprintf(stderr, "[bvh] ploc tree too deep: rebuilding with the radix tree\n");
     build_bvh_with(false, stream, d_vertices, d_indices, d_face_submesh, d_face_flags, d_o2w, n_faces, out);
   }
 }

@@ -276,3 +276,41 @@ def test_emitter_seen_from_behind(renderer, oracle):
     from conftest import rel_mse
     assert np.isfinite(got).all() and rel_mse(got, want) < 1e-3
     assert abs(got.mean() - want.mean()) < 0.01 * want.mean()
+
+
+def test_degenerate_chain_falls_back_to_the_radix_tree(renderer, oracle, monkeypatch):
+    """Triangles whose spacing grows geometrically: every cluster's nearest neighbour is the one to its left,
+    so agglomerative clustering merges one pair per round and yields a chain far deeper than the traversal
+    stack; the builder must notice and rebuild with the (depth-bounded) radix tree, and the hits must still
+    be the reference's."""
+    monkeypatch.setenv("FRD_BVH_BUILDER", "ploc")
+    k = np.arange(420, dtype=np.float64)
+    x = 1.2 ** k
+    sz = 0.04 * x
+    tris = np.stack([np.stack([x - sz, 0 * x, -sz], -1), np.stack([x + sz, 0 * x, -sz], -1), np.stack([x, 0 * x, sz], -1)], 1)
+    mat = make_material(base_color=(0.7, 0.7, 0.7))
+    s = _assemble([[(t.astype(np.float32), 0) for t in tris]], [mat])
+    o = np.stack([x, 3.0 * sz, 0 * x], -1)
+    d = np.tile(np.array([0.0, -1.0, 0.0]), (len(x), 1))
+    rays = np.concatenate([o, d], 1).astype(np.float32)
+    rays = np.concatenate([rays, random_rays(5000, 5, -50, 50)])
+    ids_g, tuv_g, ids_o, tuv_o = both(renderer, oracle, s, rays)
+    assert_identical(ids_g, tuv_g, ids_o, tuv_o, min_hits=100)   # the far triangles are beyond tmax = 1e9
+    assert renderer.accel_info()["depth"] <= 46
+
+
+def test_fallback_path_rebuilds_with_the_radix_tree(renderer, oracle, monkeypatch):
+    """The too-deep fallback itself (forced through its test hook): same tree as FRD_BVH_BUILDER=lbvh."""
+    s = scenes.standard_surface_scene(32, 16, sphere_res=(12, 6))
+    rays = random_rays(20000, 3, -10, 10)
+    monkeypatch.setenv("FRD_BVH_BUILDER", "lbvh")
+    renderer.set_scene(s)
+    renderer.build_accel()
+    want_nodes = renderer.accel_info()["n_nodes"]
+    monkeypatch.setenv("FRD_BVH_BUILDER", "ploc")
+    renderer.build_accel()
+    assert renderer.accel_info()["n_nodes"] != want_nodes
+    monkeypatch.setenv("FRD_PLOC_FORCE_FALLBACK", "1")
+    ids_g, tuv_g, ids_o, tuv_o = both(renderer, oracle, s, rays)
+    assert renderer.accel_info()["n_nodes"] == want_nodes
+    assert_identical(ids_g, tuv_g, ids_o, tuv_o, min_hits=1000)
