@@ -370,19 +370,36 @@ FR_D void trace_queue(const BvhView& bvh, Policy& pol, uint32_t* cursor, uint32_
   bool have = false;      // lane is traversing a ray
   bool finished = false;  // lane holds a finished ray that has not been retired yet
   bool exhausted = false;
+  // Work items are taken from the global cursor 32 at a time and handed out from a warp-local reserve
+  // [res_next, res_end): two refills out of three need no atomic at all, and the cursor -- one address
+  // for the whole grid -- sees a third of the traffic.
+  uint32_t res_next = 0u, res_end = 0u;  // warp-uniform
+  bool global_done = false;              // the cursor has passed n
   for (;;) {
     const uint32_t idle = __ballot_sync(0xffffffffu, !have);
     if (idle == 0xffffffffu || (!exhausted && __popc(idle) >= refill_lanes)) {
+      const uint32_t need = (uint32_t)__popc(idle);
+      const uint32_t left = res_end - res_next;
       // the cursor atomic is issued first and consumed after the retire step, so that its round
       // trip overlaps the retire step's own memory traffic (queue appends, radiance updates)
-      const bool fetch = !exhausted;
-      uint32_t base = 0;
-      if (fetch && lane == 0) base = atomicAdd(cursor, (uint32_t)__popc(idle));
+      const bool fetch = !global_done && left < need;
+      uint32_t chunk = 0;
+      if (fetch && lane == 0) chunk = atomicAdd(cursor, 32u);
       pol.retire(finished, tr.best, cnt);
       finished = false;
-      if (fetch) {
-        base = __shfl_sync(0xffffffffu, base, 0);
-        const uint32_t item = base + __popc(idle & ((1u << lane) - 1u));
+      if (!exhausted) {
+        const uint32_t k = __popc(idle & ((1u << lane) - 1u));  // this lane's rank among the idle lanes
+        uint32_t item = res_next + k;                           // from what is left of the reserve ...
+        if (fetch) {
+          chunk = __shfl_sync(0xffffffffu, chunk, 0);
+          if (k >= left) item = chunk + (k - left);             // ... then from the new chunk
+          res_next = chunk + (need - left);
+          res_end = chunk + 32u;
+          global_done = res_end >= n;
+        } else {
+          res_next += need < left ? need : left;
+          if (k >= left) item = 0xffffffffu;                    // reserve ran dry and the queue is finished
+        }
         if (!have && item < n) {
           float3 o, d;
           float tmin, tmax;
@@ -391,7 +408,7 @@ FR_D void trace_queue(const BvhView& bvh, Policy& pol, uint32_t* cursor, uint32_
           if (COUNT) cnt.nodes = cnt.tris = 0u;
           have = true;
         }
-        exhausted = base + __popc(idle) >= n;
+        exhausted = global_done && (res_next >= res_end || res_next >= n);
       }
       if (__ballot_sync(0xffffffffu, have) == 0u) break;
     }
