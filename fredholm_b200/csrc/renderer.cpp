@@ -248,7 +248,7 @@ void Renderer::Impl::build_accel()
   accel_info.n_faces = bvh.n_faces;
   accel_info.n_nodes = bvh.n_nodes;
   accel_info.depth = bvh.depth;
-  accel_info.bytes = bvh.nodes.bytes() + bvh.tris.bytes();
+  accel_info.bytes = size_t(bvh.n_nodes) * sizeof(frd::Node8) + size_t(bvh.n_faces) * 3 * sizeof(float4);
   accel_valid = true;
 }
 
