@@ -69,6 +69,9 @@ SIGNATURES = {
     "fr_stage_texture": (C.c_int, [_vp, _u8p, C.c_uint32, C.c_uint32, C.c_int]),
     "fr_set_scene_arrays": (C.c_int, [_vp, _fp, _fp, _fp, C.c_uint32, _up, _up, _up, C.c_uint32, _vp, C.c_uint32,
                                       _up, _up, _fp, C.c_uint32]),
+    "fr_scene_set_arrays": (C.c_int, [_vp, _fp, _fp, _fp, C.c_uint32, _up, _up, _up, C.c_uint32, _vp, C.c_uint32,
+                                      _up, _up, _fp, C.c_uint32]),
+    "fr_scene_validate": (C.c_int, [_vp]),
     "fr_get_scene_sizes": (C.c_int, [_vp, _up]),
     "fr_get_scene_arrays": (C.c_int, [_vp, _fp, _fp, _fp, _up, _up, _up, _vp, _up, _up, _fp, _fp]),
     "fr_get_texture_info": (C.c_int, [_vp, C.c_uint32, _up, _up, _up]),
@@ -110,6 +113,9 @@ SIGNATURES = {
     "fr_scale_layers": (C.c_int, [_vp, C.POINTER(_Layers), C.c_float]),
     "fr_get_statistics": (C.c_int, [_vp, _u64p]),
     "fr_reset_statistics": (C.c_int, [_vp]),
+    "fr_set_traversal_counting": (C.c_int, [_vp, C.c_int]),
+    "fr_get_traversal_counters": (C.c_int, [_vp, _u64p]),
+    "fr_set_samples_per_warp": (C.c_int, [_vp, C.c_uint32]),
     "fr_set_stage_timing": (C.c_int, [_vp, C.c_int]),
     "fr_get_stage_times": (C.c_int, [_vp, C.POINTER(C.c_double), _u64p]),
     "fr_event_create": (_vp, []),
@@ -328,6 +334,33 @@ def write_png(path, pixels):
     _check(lib().fr_write_png(os.fsencode(str(path)), a.ctypes.data_as(_u8p), a.shape[1], a.shape[0], a.shape[2]))
 
 
+def _scene_args(s):
+    """Argument tuple of fr_set_scene_arrays / fr_scene_set_arrays.  The C ABI sees pointers and ONE vertex /
+    face / sub-mesh count, so the per-array lengths are checked here."""
+    def arr(x, dtype, shape, what):
+        a = np.ascontiguousarray(x, dtype=dtype)
+        if a.ndim != len(shape) or any(d is not None and a.shape[i] != d for i, d in enumerate(shape)):
+            raise FredholmError("invalid scene: %s has shape %s" % (what, a.shape))
+        return a
+    v = arr(s.vertices, np.float32, (None, 3), "vertices")
+    n = arr(s.normals, np.float32, (len(v), 3), "normals")
+    t = arr(s.texcoords, np.float32, (len(v), 2), "texcoords")
+    idx = arr(s.indices, np.uint32, (None, 3), "indices")
+    mid = arr(s.material_ids, np.uint32, (len(idx),), "material_ids")
+    iid = arr(s.instance_ids, np.uint32, (len(idx),), "instance_ids")
+    so = arr(s.submesh_offsets, np.uint32, (None,), "submesh_offsets")
+    sn = arr(s.submesh_n_faces, np.uint32, (len(so),), "submesh_n_faces")
+    tr = arr(np.asarray(s.transforms, dtype=np.float32).reshape(-1, 16), np.float32, (len(so), 16), "transforms")
+    mats = np.ascontiguousarray(s.materials)
+    if mats.dtype.itemsize != 180:
+        raise FredholmError("invalid scene: materials must be 180-byte records")
+    keep = (v, n, t, idx, mid, iid, so, sn, tr, mats)
+    args = (_f(v), _f(n), _f(t), len(v), _u(idx), _u(mid), _u(iid), len(idx), mats.ctypes.data_as(_vp), len(mats),
+            _u(so), _u(sn), _f(tr), len(so))
+    _scene_args.keepalive = keep  # the arrays must outlive the call that follows
+    return args
+
+
 class Scene:
     """Host-side fredholm::Scene (file loaders, animation); needs no GPU."""
 
@@ -344,6 +377,13 @@ class Scene:
 
     def update_animation(self, t):
         _check(lib().fr_scene_update_animation(self._h, float(t)))
+
+    def set_arrays(self, s: "SceneArrays"):
+        _check(lib().fr_scene_set_arrays(self._h, *_scene_args(s)))
+
+    def validate(self):
+        """Scene::validate: raises FredholmError("invalid scene: ...") on any out-of-range index."""
+        _check(lib().fr_scene_validate(self._h))
 
     def close(self):
         if getattr(self, "_h", None):
@@ -390,11 +430,7 @@ class Renderer:
             if L.fr_stage_texture(self._h, img.ctypes.data_as(_u8p), img.shape[1], img.shape[0],
                                   1 if is_color else 0) < 0:
                 raise FredholmError(L.fr_last_error().decode())
-        _check(L.fr_set_scene_arrays(
-            self._h, _f(s.vertices), _f(s.normals), _f(s.texcoords), len(s.vertices), _u(s.indices),
-            _u(s.material_ids), _u(s.instance_ids), len(s.indices), s.materials.ctypes.data_as(_vp),
-            len(s.materials), _u(s.submesh_offsets), _u(s.submesh_n_faces), _f(s.transforms),
-            len(s.submesh_offsets)))
+        _check(L.fr_set_scene_arrays(self._h, *_scene_args(s)))
 
     def get_scene(self) -> SceneArrays:
         L = lib()
@@ -576,6 +612,19 @@ class Renderer:
 
     def reset_statistics(self):
         _check(lib().fr_reset_statistics(self._h))
+
+    def set_traversal_counting(self, on=True):
+        """Measurement: counting instantiations of the traversal kernels (process-wide)."""
+        _check(lib().fr_set_traversal_counting(self._h, 1 if on else 0))
+
+    def traversal_counters(self):
+        """{ray type: (nodes visited, triangles tested)} since the last reset (counting mode only)."""
+        out = np.zeros(6, np.uint64)
+        _check(lib().fr_get_traversal_counters(self._h, out.ctypes.data_as(_u64p)))
+        return {k: (int(out[i]), int(out[3 + i])) for i, k in enumerate(("radiance", "shadow", "light"))}
+
+    def set_samples_per_warp(self, spw):
+        _check(lib().fr_set_samples_per_warp(self._h, int(spw)))
 
     def stream(self):
         return int(lib().fr_get_stream(self._h))

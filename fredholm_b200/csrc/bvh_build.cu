@@ -14,6 +14,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
+#include <stdexcept>
 
 #include "bvh_build.h"
 
@@ -567,6 +569,11 @@ __global__ void k_empty_root(Node8* nodes)
 struct TreeTooDeep : std::runtime_error {
   TreeTooDeep() : std::runtime_error("bvh: tree too deep for the traversal stack") {}
 };
+// a PLOC round that merged nothing (cannot happen with the symmetric tie break, kept as a guard): the
+// caller rebuilds with the radix tree, like TreeTooDeep
+struct PlocStalled : std::runtime_error {
+  PlocStalled() : std::runtime_error("bvh ploc: no progress") {}
+};
 
 // builder selection (experiments / fallback): FRD_BVH_BUILDER=lbvh|ploc, FRD_PLOC_RADIUS=1..32
 bool builder_is_ploc()
@@ -604,22 +611,57 @@ struct PhaseClock {
 
 namespace
 {
-// Build temporaries come from the device's stream-ordered memory pool (cudaMallocAsync) with the release
-// threshold lifted, so a rebuild -- set_time on an animated scene -- reuses the pool's memory instead of paying
-// cudaMalloc / cudaFree for every buffer (these calls were 20-90 ms of a 52 M-triangle build).
+// Build temporaries come from a PRIVATE stream-ordered memory pool per device (cudaMemPoolCreate +
+// cudaMallocFromPoolAsync) with the release threshold lifted, so a rebuild -- set_time on an animated scene --
+// reuses the pool's memory instead of paying cudaMalloc / cudaFree for every buffer (these calls were 20-90 ms
+// of a 52 M-triangle build).  The device's default pool, which the host application may share (e.g. PyTorch's
+// cudaMallocAsync backend), is never touched.  What the pool keeps between builds: nothing after the first
+// build of a device (static scenes give everything back), up to FRD_BVH_POOL_KEEP_GB (default 16) after a
+// rebuild.
 thread_local cudaStream_t g_scratch_stream = nullptr;
+thread_local cudaMemPool_t g_scratch_pool = nullptr;
+
+constexpr int kMaxDevices = 64;
+std::mutex g_pool_mutex;
+cudaMemPool_t g_pools[kMaxDevices] = {};
+unsigned g_builds[kMaxDevices] = {};
+
+int current_device()
+{
+  int dev = 0;
+  FR_CUDA_CHECK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= kMaxDevices) throw std::runtime_error("bvh: device index out of range");
+  return dev;
+}
 
 void init_scratch_pool()
 {
-  static thread_local int ready_for_device = -1;
+  const int dev = current_device();
+  std::lock_guard<std::mutex> lock(g_pool_mutex);
+  if (!g_pools[dev]) {
+    cudaMemPoolProps props = {};
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = dev;
+    FR_CUDA_CHECK(cudaMemPoolCreate(&g_pools[dev], &props));
+    uint64_t keep = UINT64_MAX;
+    FR_CUDA_CHECK(cudaMemPoolSetAttribute(g_pools[dev], cudaMemPoolAttrReleaseThreshold, &keep));
+  }
+  g_scratch_pool = g_pools[dev];
+}
+
+// after a build: give the temporaries back (first build) or keep them for the next rebuild
+void trim_scratch_pool()
+{
   int dev = 0;
-  FR_CUDA_CHECK(cudaGetDevice(&dev));
-  if (ready_for_device == dev) return;
-  cudaMemPool_t pool;
-  FR_CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, dev));
-  uint64_t keep = UINT64_MAX;
-  FR_CUDA_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
-  ready_for_device = dev;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return;
+  std::lock_guard<std::mutex> lock(g_pool_mutex);
+  if (!g_pools[dev]) return;
+  const char* e = getenv("FRD_BVH_POOL_KEEP_GB");
+  const size_t keep_gb = e ? (size_t)strtoull(e, nullptr, 0) : 16;
+  const size_t keep = g_builds[dev]++ == 0 ? 0 : keep_gb << 30;
+  cudaMemPoolTrimTo(g_pools[dev], keep);
 }
 
 template <typename T>
@@ -634,8 +676,8 @@ class ScratchBuf
   void alloc(size_t n)
   {
     release();
+    if (n) FR_CUDA_CHECK(cudaMallocFromPoolAsync(reinterpret_cast<void**>(&p_), n * sizeof(T), g_scratch_pool, g_scratch_stream));
     n_ = n;
-    if (n) FR_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void**>(&p_), n * sizeof(T), g_scratch_stream));
   }
   void release()
   {
@@ -732,7 +774,7 @@ void build_bvh_with(bool use_ploc, cudaStream_t stream, const float3* d_vertices
       uint32_t c_next = 0;
       FR_CUDA_CHECK(cudaMemcpyAsync(&c_next, n_selected, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
       FR_CUDA_CHECK(cudaStreamSynchronize(stream));
-      if (c_next >= c) throw std::runtime_error("bvh ploc: no progress");
+      if (c_next >= c) throw PlocStalled();
       c = c_next;
       out.ploc_rounds++;
     }
@@ -809,23 +851,22 @@ void build_bvh(cudaStream_t stream, const float3* d_vertices, const uint3* d_ind
                const fredholm::Matrix3x4* d_o2w, uint32_t n_faces, DeviceBvh& out)
 {
   const bool ploc = builder_is_ploc();
-  // the pool keeps at most 16 GB between builds (a 52 M-triangle build uses ~10 GB of temporaries)
+  // a 52 M-triangle build uses ~10 GB of temporaries (trim_scratch_pool: what stays cached afterwards)
   struct TrimPool {
-    ~TrimPool()
-    {
-      int dev = 0;
-      cudaMemPool_t pool;
-      if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess)
-        cudaMemPoolTrimTo(pool, size_t(16) << 30);
-    }
+    ~TrimPool() { trim_scratch_pool(); }
   } trim_on_exit;
+  auto rebuild_with_radix_tree = [&](const char* why) {
+    // an agglomerative tree has no depth bound; the radix tree's depth is bounded by the 63 key bits
+    if (!ploc) throw;
+    if (getenv("FRD_BVH_VERBOSE")) fprintf(stderr, "[bvh] ploc %s: rebuilding with the radix tree\n", why);
+    build_bvh_with(false, stream, d_vertices, d_indices, d_face_submesh, d_face_flags, d_o2w, n_faces, out);
+  };
   try {
     build_bvh_with(ploc, stream, d_vertices, d_indices, d_face_submesh, d_face_flags, d_o2w, n_faces, out);
   } catch (const TreeTooDeep&) {
-    // an agglomerative tree has no depth bound; the radix tree's depth is bounded by the 63 key bits
-    if (!ploc) throw;
-    if (getenv("FRD_BVH_VERBOSE")) fprintf(stderr, "[bvh] ploc tree too deep: rebuilding with the radix tree\n");
-    build_bvh_with(false, stream, d_vertices, d_indices, d_face_submesh, d_face_flags, d_o2w, n_faces, out);
+    rebuild_with_radix_tree("tree too deep");
+  } catch (const PlocStalled&) {
+    rebuild_with_radix_tree("made no progress");
   }
 }
 

@@ -155,6 +155,33 @@ int fr_stage_texture(fr_renderer* r, const uint8_t* rgba8, uint32_t width, uint3
   return rc == 0 ? id : -1;
 }
 
+static void fill_scene(Scene& s, const float* vertices, const float* normals, const float* texcoords,
+                       uint32_t n_vertices, const uint32_t* indices, const uint32_t* material_ids,
+                       const uint32_t* instance_ids, uint32_t n_faces, const void* materials, uint32_t n_materials,
+                       const uint32_t* submesh_offsets, const uint32_t* submesh_n_faces, const float* transforms,
+                       uint32_t n_submeshes)
+{
+  if (!vertices || !normals || !texcoords || !indices || !material_ids || !instance_ids || !materials ||
+      !submesh_offsets || !submesh_n_faces || !transforms)
+    throw std::runtime_error("invalid scene: null array");
+  s.m_vertices.resize(n_vertices);
+  s.m_normals.resize(n_vertices);
+  s.m_texcoords.resize(n_vertices);
+  std::memcpy(s.m_vertices.data(), vertices, sizeof(float3) * n_vertices);
+  std::memcpy(s.m_normals.data(), normals, sizeof(float3) * n_vertices);
+  std::memcpy(s.m_texcoords.data(), texcoords, sizeof(float2) * n_vertices);
+  s.m_indices.resize(n_faces);
+  std::memcpy(s.m_indices.data(), indices, sizeof(uint3) * n_faces);
+  s.m_material_ids.assign(material_ids, material_ids + n_faces);
+  s.m_instance_ids.assign(instance_ids, instance_ids + n_faces);
+  s.m_materials.resize(n_materials);
+  std::memcpy(s.m_materials.data(), materials, sizeof(Material) * n_materials);
+  s.m_submesh_offsets.assign(submesh_offsets, submesh_offsets + n_submeshes);
+  s.m_submesh_n_faces.assign(submesh_n_faces, submesh_n_faces + n_submeshes);
+  s.m_transforms.resize(n_submeshes);
+  std::memcpy(s.m_transforms.data(), transforms, sizeof(float) * 16 * n_submeshes);
+}
+
 int fr_set_scene_arrays(fr_renderer* r, const float* vertices, const float* normals, const float* texcoords,
                         uint32_t n_vertices, const uint32_t* indices, const uint32_t* material_ids,
                         const uint32_t* instance_ids, uint32_t n_faces, const void* materials, uint32_t n_materials,
@@ -163,22 +190,8 @@ int fr_set_scene_arrays(fr_renderer* r, const float* vertices, const float* norm
 {
   return guarded([&] {
     Scene s;
-    s.m_vertices.resize(n_vertices);
-    s.m_normals.resize(n_vertices);
-    s.m_texcoords.resize(n_vertices);
-    std::memcpy(s.m_vertices.data(), vertices, sizeof(float3) * n_vertices);
-    std::memcpy(s.m_normals.data(), normals, sizeof(float3) * n_vertices);
-    std::memcpy(s.m_texcoords.data(), texcoords, sizeof(float2) * n_vertices);
-    s.m_indices.resize(n_faces);
-    std::memcpy(s.m_indices.data(), indices, sizeof(uint3) * n_faces);
-    s.m_material_ids.assign(material_ids, material_ids + n_faces);
-    s.m_instance_ids.assign(instance_ids, instance_ids + n_faces);
-    s.m_materials.resize(n_materials);
-    std::memcpy(s.m_materials.data(), materials, sizeof(Material) * n_materials);
-    s.m_submesh_offsets.assign(submesh_offsets, submesh_offsets + n_submeshes);
-    s.m_submesh_n_faces.assign(submesh_n_faces, submesh_n_faces + n_submeshes);
-    s.m_transforms.resize(n_submeshes);
-    std::memcpy(s.m_transforms.data(), transforms, sizeof(float) * 16 * n_submeshes);
+    fill_scene(s, vertices, normals, texcoords, n_vertices, indices, material_ids, instance_ids, n_faces, materials,
+               n_materials, submesh_offsets, submesh_n_faces, transforms, n_submeshes);
     s.m_textures = std::move(r->staged_textures);
     r->staged_textures.clear();
     r->renderer.set_scene(s);
@@ -223,6 +236,22 @@ int fr_scene_load(fr_scene* s, const char* path, int clear)
     s->scene.load_model(path, clear != 0);
     if (!s->scene.is_valid()) throw std::runtime_error("invalid scene");
   });
+}
+int fr_scene_set_arrays(fr_scene* s, const float* vertices, const float* normals, const float* texcoords,
+                        uint32_t n_vertices, const uint32_t* indices, const uint32_t* material_ids,
+                        const uint32_t* instance_ids, uint32_t n_faces, const void* materials, uint32_t n_materials,
+                        const uint32_t* submesh_offsets, const uint32_t* submesh_n_faces, const float* transforms,
+                        uint32_t n_submeshes)
+{
+  return guarded([&] {
+    s->scene.clear();
+    fill_scene(s->scene, vertices, normals, texcoords, n_vertices, indices, material_ids, instance_ids, n_faces,
+               materials, n_materials, submesh_offsets, submesh_n_faces, transforms, n_submeshes);
+  });
+}
+int fr_scene_validate(const fr_scene* s)
+{
+  return guarded([&] { s->scene.validate(); });
 }
 int fr_scene_get_sizes(fr_scene* s, uint32_t* out6)
 {
@@ -434,6 +463,24 @@ int fr_get_statistics(fr_renderer* r, uint64_t* out5)
     out5[3] = s.rays_light;
     out5[4] = s.kernel_launches;
   });
+}
+int fr_set_traversal_counting(fr_renderer* r, int on)
+{
+  return guarded([&] { r->renderer.set_traversal_counting(on != 0); });
+}
+int fr_get_traversal_counters(fr_renderer* r, uint64_t* out6)
+{
+  return guarded([&] {
+    const RenderStatistics s = r->renderer.get_statistics();
+    for (int i = 0; i < 3; ++i) {
+      out6[i] = s.nodes_visited[i];
+      out6[3 + i] = s.tris_tested[i];
+    }
+  });
+}
+int fr_set_samples_per_warp(fr_renderer* r, uint32_t spw)
+{
+  return guarded([&] { r->renderer.set_samples_per_warp(spw); });
 }
 int fr_reset_statistics(fr_renderer* r)
 {

@@ -56,8 +56,19 @@ class DevBuf
   void alloc(size_t n)
   {
     release();
-    n_ = n;
-    if (n) FR_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&p_), n * sizeof(T)));
+    if (n) {
+      // size and pointer change together: a failed cudaMalloc leaves an EMPTY buffer, never {nullptr, n}
+      T* p = nullptr;
+      const cudaError_t err = cudaMalloc(reinterpret_cast<void**>(&p), n * sizeof(T));
+      if (err != cudaSuccess) {
+        cudaGetLastError();  // clear the sticky-free error so the context stays usable
+        std::stringstream ss;
+        ss << "cudaMalloc of " << n * sizeof(T) << " bytes failed: '" << cudaGetErrorString(err) << "'";
+        throw std::runtime_error(ss.str());
+      }
+      p_ = p;
+      n_ = n;
+    }
   }
   // grow-only (contents are NOT preserved)
   void reserve(size_t n)

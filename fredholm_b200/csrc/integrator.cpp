@@ -19,6 +19,14 @@ Integrator::Integrator(cudaStream_t stream) : m_stream(stream)
 {
   m_sort_mask = env_u32("FRD_SORT", 0u);
   m_sort_bits = std::min(std::max(env_u32("FRD_SORT_BITS", 4u), 1u), 7u);
+  set_samples_per_warp(env_u32("FRD_SAMPLES_PER_WARP", kDefaultSamplesPerWarp));
+}
+
+void Integrator::set_samples_per_warp(uint32_t spw)
+{
+  uint32_t l = 0;
+  while (l < 5u && (2u << l) <= spw) l++;
+  m_spw_log2 = l;
 }
 
 void Integrator::set_coherence_sort(uint32_t queue_mask, uint32_t cell_bits)
@@ -106,6 +114,42 @@ void Integrator::ensure_capacity(size_t n_slots)
   if (n_slots <= m_capacity) return;
   // buffers are in use by work already queued on the stream
   FR_CUDA_CHECK(cudaStreamSynchronize(m_stream));
+  // Not valid until every buffer below has its new size: if one allocation throws (a 64 Mi-path wave is ~25 GB),
+  // the capacity stays 0 and all wave buffers are released, so a later render() with a smaller wave reallocates
+  // everything instead of launching on a half-grown set.
+  m_capacity = 0;
+  try {
+    grow_wave_buffers(n_slots);
+  } catch (...) {
+    release_wave_buffers();
+    throw;
+  }
+  m_capacity = n_slots;
+  m_state_bytes = n_slots * kWaveBytesPerSlot;
+}
+
+void Integrator::release_wave_buffers()
+{
+  m_ray_o.release();
+  m_ray_d.release();
+  m_hit.release();
+  m_thr.release();
+  m_L.release();
+  m_aov0.release();
+  m_aov1.release();
+  m_aov2.release();
+  m_queue[0].release();
+  m_queue[1].release();
+  for (auto& s : m_shadow) s.release();
+  for (auto& q : m_class_queue) q.release();
+  m_light.release();
+  m_sort_keys.release();
+  m_sort_out.release();
+  m_state_bytes = 0;
+}
+
+void Integrator::grow_wave_buffers(size_t n_slots)
+{
   m_ray_o.alloc(n_slots);
   m_ray_d.alloc(n_slots);
   m_hit.alloc(n_slots);
@@ -121,9 +165,6 @@ void Integrator::ensure_capacity(size_t n_slots)
   m_light.alloc(n_slots);
   m_sort_keys.alloc(n_slots);
   m_sort_out.alloc(n_slots);
-  m_capacity = n_slots;
-  m_state_bytes = n_slots * (8 * sizeof(float4) + (2 + CLS_COUNT) * sizeof(uint32_t) + 3 * sizeof(ShadowRay) +
-                             sizeof(LightRay) + 2 * sizeof(uint32_t));
 }
 
 void Integrator::render(const SceneView& scene, const fredholm::CameraParams& camera, uint32_t width,
@@ -131,10 +172,22 @@ void Integrator::render(const SceneView& scene, const fredholm::CameraParams& ca
                         uint32_t n_samples, uint32_t max_depth, uint32_t seed, int film_mode, uint32_t class_mask)
 {
   if (width == 0 || height == 0 || n_samples == 0) return;
-  const FilmGeom film = make_film_geom(width, height);
-  const uint32_t per_wave =
-      (uint32_t)std::max<size_t>(1, std::min<size_t>(n_samples, m_max_wave_paths / film.slots_per_sample));
-  ensure_capacity((size_t)per_wave * film.slots_per_sample);
+  // samples per warp: never more than the call's sample count needs (a 1-spp render keeps 8x4 tiles)
+  uint32_t spw_log2 = m_spw_log2;
+  while (spw_log2 > 0 && (1u << spw_log2) > n_samples) spw_log2--;
+  const FilmGeom film = make_film_geom(width, height, spw_log2);
+  // a wave = whole sample groups (spw samples of every pixel), at least one
+  size_t groups_per_wave = std::max<size_t>(
+      1, std::min<size_t>(film_groups(film, n_samples), m_max_wave_paths / film.slots_per_group));
+  if (groups_per_wave * film.slots_per_group > m_capacity) {
+    // growing: never ask for more than the device can give (90 % of what is free plus what the wave holds now)
+    size_t free_b = 0, total_b = 0;
+    FR_CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
+    const size_t fit = (size_t)(0.9 * (double)(free_b + m_state_bytes)) / (kWaveBytesPerSlot * film.slots_per_group);
+    groups_per_wave = std::max<size_t>(1, std::min(groups_per_wave, fit));
+  }
+  const uint32_t per_wave = (uint32_t)(groups_per_wave << spw_log2);
+  ensure_capacity(groups_per_wave * film.slots_per_group);
 
   WaveBuffers wb;
   wb.ray_o = m_ray_o.get();
@@ -230,6 +283,10 @@ RenderStats Integrator::stats()
   s.rays_closest = h.rays_closest;
   s.rays_shadow = h.rays_shadow;
   s.rays_light = h.rays_light;
+  for (int i = 0; i < 3; ++i) {
+    s.nodes[i] = h.nodes[i];
+    s.tris[i] = h.tris[i];
+  }
   return s;
 }
 

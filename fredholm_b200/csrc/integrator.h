@@ -18,6 +18,8 @@ struct RenderStats {
   unsigned long long rays_shadow = 0;   // visibility rays traced
   unsigned long long rays_light = 0;    // MIS rays traced
   unsigned long long launches = 0;      // kernels launched by the integrator
+  // counting builds (set_traversal_counting): nodes visited / triangles tested per ray type
+  unsigned long long nodes[3] = {0, 0, 0}, tris[3] = {0, 0, 0};
 };
 
 enum Stage : int {
@@ -48,6 +50,11 @@ class Integrator
   void set_single_launch(bool on) { m_single_launch = on; }
   bool single_launch() const { return m_single_launch; }
   size_t max_wave_paths() const { return m_max_wave_paths; }
+  // samples of one pixel block that share a warp (1, 2, 4, ... 32; wavefront.h FilmGeom): camera rays and
+  // first-bounce shadow rays of a warp then form a one-pixel beam.  Does not change any sample's value.
+  void set_samples_per_warp(uint32_t spw);
+  uint32_t samples_per_warp() const { return 1u << m_spw_log2; }
+  static constexpr uint32_t kDefaultSamplesPerWarp = 1;
 
   // Renders samples [sample_base, sample_base + n_samples) of every pixel into
   // `layers` (device pointers).  Asynchronous on the stream.  class_mask: bit c set if
@@ -76,11 +83,17 @@ class Integrator
   ~Integrator();
 
  private:
+  // wave state per path slot: 8 float4 words, 2 + CLS_COUNT queue entries, 3 shadow + 1 MIS ray records, sort scratch
+  static constexpr size_t kWaveBytesPerSlot = 8 * sizeof(float4) + (2 + CLS_COUNT) * sizeof(uint32_t) +
+                                              3 * sizeof(ShadowRay) + sizeof(LightRay) + 2 * sizeof(uint32_t);
   void ensure_capacity(size_t n_slots);
+  void grow_wave_buffers(size_t n_slots);
+  void release_wave_buffers();
 
   cudaStream_t m_stream;
   size_t m_max_wave_paths = size_t(1) << 26;  // 64 Mi paths (24 GB of wave state)
   size_t m_capacity = 0;
+  uint32_t m_spw_log2 = 0;
   size_t m_state_bytes = 0;
   unsigned long long m_launches = 0;
 

@@ -193,11 +193,17 @@ float exposure_from_iso(float ISO)
   return 1.0f / max_luminance;
 }
 
+// bloom scratch: one buffer per (thread, device) -- a renderer on a second device of the same thread must not
+// be handed a pointer that lives on the first
 frd::DevBuf<float4>& scratch(size_t n)
 {
-  static thread_local frd::DevBuf<float4> buf;
-  buf.reserve(n);
-  return buf;
+  constexpr int kMaxDevices = 64;
+  static thread_local frd::DevBuf<float4> buf[kMaxDevices];
+  int dev = 0;
+  FR_CUDA_CHECK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= kMaxDevices) throw std::runtime_error("post-process: device index out of range");
+  buf[dev].reserve(n);
+  return buf[dev];
 }
 
 void launch_tone_map(const float4* in, int width, int height, float ISO, float ca, float4* out, cudaStream_t s)

@@ -161,6 +161,7 @@ void Renderer::Impl::upload_transforms()
 void Renderer::Impl::upload_scene()
 {
   const Scene& s = scene;
+  s.validate();
   FR_CUDA_CHECK(cudaStreamSynchronize(stream));
   d_vertices.upload(s.m_vertices, stream);
   d_normals.upload(s.m_normals, stream);
@@ -440,6 +441,10 @@ void Renderer::render(const CameraParams& camera, const float3& bg_color, const 
                       uint32_t n_samples, uint32_t max_depth)
 {
   FR_CUDA_CHECK(cudaSetDevice(m_impl->device));
+  // A path draws up to four 1-D Sobol dimensions per bounce (light choice, two lobe choices, roulette) after
+  // dimension 1 of the camera ray, and the table has 1024 dimensions (sobol.cu; the reference reads past it
+  // beyond that, pt.cu:455-471 has no bound): 2 + 4 * max_depth <= 1024.
+  if (max_depth > 255u) throw std::invalid_argument("render: max_depth must be <= 255 (1024 Sobol dimensions)");
   if (!m_impl->accel_valid) m_impl->build_accel();
   const frd::SceneView view = m_impl->view(bg_color);
   m_impl->integrator->render(view, camera, m_impl->width, m_impl->height, render_layer, m_impl->sample_count,
@@ -465,6 +470,8 @@ void Renderer::scale_layers(const RenderLayer& render_layer, float scale)
 }
 void Renderer::set_max_wave_paths(size_t n_paths) { m_impl->integrator->set_max_wave_paths(n_paths); }
 void Renderer::set_single_launch(bool on) { m_impl->integrator->set_single_launch(on); }
+void Renderer::set_samples_per_warp(uint32_t spw) { m_impl->integrator->set_samples_per_warp(spw); }
+void Renderer::set_traversal_counting(bool on) { frd::set_traversal_counting(on); }
 
 void Renderer::set_stage_timing(bool on) { m_impl->integrator->set_stage_timing(on); }
 void Renderer::get_stage_times(double ms[kStageCount], unsigned long long launches[kStageCount])
@@ -486,6 +493,10 @@ RenderStatistics Renderer::get_statistics()
   r.rays_shadow = s.rays_shadow;
   r.rays_light = s.rays_light;
   r.kernel_launches = s.launches;
+  for (int i = 0; i < 3; ++i) {
+    r.nodes_visited[i] = s.nodes[i];
+    r.tris_tested[i] = s.tris[i];
+  }
   return r;
 }
 void Renderer::reset_statistics() { m_impl->integrator->reset_stats(); }

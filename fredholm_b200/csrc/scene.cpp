@@ -432,6 +432,57 @@ bool Scene::is_valid() const
   return m_submesh_offsets.size() > 0 && m_vertices.size() > 0 && m_indices.size() > 0;
 }
 
+// Everything the kernels index with scene data is checked here once, on the host, so that a malformed scene
+// (hand-filled arrays through fr_set_scene_arrays / set_scene, a glTF primitive without NORMAL or TEXCOORD_0)
+// throws "invalid scene: ..." instead of reading outside a device buffer.
+void Scene::validate() const
+{
+  const Scene& s = *this;
+  auto fail = [](const std::string& what) { throw std::runtime_error("invalid scene: " + what); };
+  const size_t nv = s.m_vertices.size(), nf = s.m_indices.size(), nsm = s.m_submesh_offsets.size();
+  if (nv == 0 || nf == 0) fail("no geometry");
+  if (s.m_normals.size() != nv) fail("normals.size() != vertices.size()");
+  if (s.m_texcoords.size() != nv) fail("texcoords.size() != vertices.size()");
+  if (s.m_material_ids.size() != nf) fail("material_ids.size() != number of faces");
+  if (s.m_instance_ids.size() != nf) fail("instance_ids.size() != number of faces");
+  if (s.m_submesh_n_faces.size() != nsm) fail("submesh_offsets / submesh_n_faces differ in length");
+  if (s.m_transforms.size() != nsm) fail("transforms.size() != number of sub-meshes");
+  if (nsm == 0) fail("no sub-mesh");
+  for (size_t f = 0; f < nf; ++f) {
+    const uint3 i = s.m_indices[f];
+    if (i.x >= nv || i.y >= nv || i.z >= nv) fail("vertex index out of range in face " + std::to_string(f));
+    if (s.m_material_ids[f] >= s.m_materials.size()) fail("face without a valid material");
+    if (s.m_instance_ids[f] >= nsm) fail("instance id out of range in face " + std::to_string(f));
+  }
+  // the sub-meshes must tile the face range: every face belongs to exactly one
+  std::vector<uint8_t> covered(nf, 0);
+  for (size_t sm = 0; sm < nsm; ++sm) {
+    const uint64_t o = s.m_submesh_offsets[sm], n = s.m_submesh_n_faces[sm];
+    if (o + n > nf) fail("sub-mesh " + std::to_string(sm) + " exceeds the face array");
+    for (uint64_t f = o; f < o + n; ++f) {
+      if (covered[f]) fail("sub-meshes overlap at face " + std::to_string(f));
+      covered[f] = 1;
+    }
+  }
+  for (size_t f = 0; f < nf; ++f)
+    if (!covered[f]) fail("face " + std::to_string(f) + " belongs to no sub-mesh");
+  const int nt = (int)s.m_textures.size();
+  for (size_t m = 0; m < s.m_materials.size(); ++m) {
+    const Material& mt = s.m_materials[m];
+    const int ids[] = {mt.base_color_texture_id, mt.specular_color_texture_id, mt.specular_roughness_texture_id,
+                       mt.metalness_texture_id, mt.metallic_roughness_texture_id, mt.coat_texture_id,
+                       mt.coat_roughness_texture_id, mt.emission_texture_id, mt.heightmap_texture_id,
+                       mt.normalmap_texture_id, mt.alpha_texture_id};
+    for (int id : ids)
+      if (id < -1 || id >= nt) fail("texture id " + std::to_string(id) + " out of range in material " + std::to_string(m));
+  }
+  for (size_t t = 0; t < s.m_textures.size(); ++t) {
+    const Texture& tx = s.m_textures[t];
+    if (tx.m_width == 0 || tx.m_height == 0 || tx.m_data.size() != (size_t)tx.m_width * tx.m_height)
+      fail("texture " + std::to_string(t) + " has no texels or a wrong size");
+  }
+}
+
 void Scene::clear() { *this = Scene(); }
 
 void Scene::load_model(const std::filesystem::path& filepath, bool do_clear)

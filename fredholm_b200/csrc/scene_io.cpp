@@ -448,10 +448,16 @@ struct GltfLoader {
   int indices_offset = 0;
   int prev_indices_size = 0;
 
-  Node load_node(int node_idx)
+  std::vector<uint8_t> on_path;  // nodes of the current root-to-node chain (cycle guard)
+
+  Node load_node(int node_idx, int depth = 0)
   {
     const auto& nodes = model.root.array("nodes");
     if (node_idx < 0 || node_idx >= (int)nodes.size()) throw std::runtime_error("node index out of range");
+    // a glTF node hierarchy is a forest; a file that lists an ancestor as a child would recurse for ever
+    if (on_path.size() != nodes.size()) on_path.assign(nodes.size(), 0);
+    if (on_path[node_idx] || depth > 256) throw std::runtime_error("node hierarchy has a cycle or is too deep");
+    on_path[node_idx] = 1;
     const Json& node = nodes[node_idx];
     Node n;
     n.idx = node_idx;
@@ -524,6 +530,32 @@ struct GltfLoader {
             }
           }
         }
+        // A primitive without NORMAL / TEXCOORD_0 leaves those arrays shorter than the vertex array (the reference
+        // does the same and then reads out of bounds on the device): pad them, with area-weighted vertex normals
+        // of this primitive's triangles and zero texture coordinates.
+        if (sc.m_normals.size() < sc.m_vertices.size()) {
+          const size_t first = sc.m_normals.size();
+          sc.m_normals.resize(sc.m_vertices.size(), make_float3(0.f, 0.f, 0.f));
+          for (size_t f = sc.m_indices.size() - (size_t)n_tris; f < sc.m_indices.size(); ++f) {
+            const uint3 t = sc.m_indices[f];
+            if (t.x >= sc.m_vertices.size() || t.y >= sc.m_vertices.size() || t.z >= sc.m_vertices.size()) continue;
+            const float3 a = sc.m_vertices[t.x], b = sc.m_vertices[t.y], c = sc.m_vertices[t.z];
+            const float3 e1 = make_float3(b.x - a.x, b.y - a.y, b.z - a.z), e2 = make_float3(c.x - a.x, c.y - a.y, c.z - a.z);
+            const float3 n = make_float3(e1.y * e2.z - e1.z * e2.y, e1.z * e2.x - e1.x * e2.z, e1.x * e2.y - e1.y * e2.x);
+            for (uint32_t v : {t.x, t.y, t.z})
+              if (v >= first) {
+                sc.m_normals[v].x += n.x;
+                sc.m_normals[v].y += n.y;
+                sc.m_normals[v].z += n.z;
+              }
+          }
+          for (size_t v = first; v < sc.m_normals.size(); ++v) {
+            float3& n = sc.m_normals[v];
+            const float len = std::sqrt(n.x * n.x + n.y * n.y + n.z * n.z);
+            n = len > 0.f ? make_float3(n.x / len, n.y / len, n.z / len) : make_float3(0.f, 1.f, 0.f);
+          }
+        }
+        if (sc.m_texcoords.size() < sc.m_vertices.size()) sc.m_texcoords.resize(sc.m_vertices.size(), make_float2(0.f, 0.f));
         const unsigned int material = (unsigned int)prim.integer("material", -1);
         for (int i = 0; i < n_tris; ++i) sc.m_material_ids.push_back(material);
         for (int i = 0; i < n_tris; ++i) sc.m_instance_ids.push_back((unsigned int)sc.m_submesh_offsets.size());
@@ -535,7 +567,8 @@ struct GltfLoader {
     } else {
       n.submesh_id = -1;
     }
-    for (const Json& child : node.array("children")) n.children.push_back(load_node((int)child.num));
+    for (const Json& child : node.array("children")) n.children.push_back(load_node((int)child.num, depth + 1));
+    on_path[node_idx] = 0;
     return n;
   }
 };

@@ -33,11 +33,11 @@ constexpr int kBlock = 128;
 
 FR_D float pack_draws(const PathSampler& s) { return __uint_as_float(s.cmj_draws | (s.sobol_dim << 16)); }
 
-FR_D PathSampler restore_sampler(const WaveParams& wp, uint32_t slot, uint32_t x, uint32_t y, float packed)
+FR_D PathSampler restore_sampler(const WaveParams& wp, uint32_t sample, uint32_t x, uint32_t y, float packed)
 {
   PathSampler s;
   const uint32_t n_pixels = wp.film.width * wp.film.height;
-  s.init(x + wp.film.width * y, wp.sample_base + slot / wp.film.slots_per_sample, n_pixels, wp.seed);
+  s.init(x + wp.film.width * y, wp.sample_base + sample, n_pixels, wp.seed);
   const uint32_t bits = __float_as_uint(packed);
   s.cmj_draws = bits & 0xffffu;
   s.sobol_dim = bits >> 16;
@@ -50,11 +50,11 @@ constexpr int kGenBlock = 256;
 __global__ void __launch_bounds__(kGenBlock) k_generate(WaveParams wp, WaveBuffers wb)
 {
   const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
-  const uint32_t n_slots = wp.n_samples * wp.film.slots_per_sample;
+  const uint32_t n_slots = film_groups(wp.film, wp.n_samples) * wp.film.slots_per_group;
   bool alive = false;
   if (slot < n_slots) {
-    uint32_t x, y;
-    const bool inside = slot_to_pixel(wp.film, slot % wp.film.slots_per_sample, x, y);
+    uint32_t x, y, sample;
+    const bool inside = slot_to_pixel(wp.film, slot, x, y, sample) && sample < wp.n_samples;
     wb.L[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (wp.single_launch) wb.hit[slot] = make_float4(0.f, 0.f, 0.f, __uint_as_float(kNoHit));  // read by k_first_hit
     if (wp.want_aov) {  // the first-hit words are only kept when a layer will read them
@@ -64,8 +64,7 @@ __global__ void __launch_bounds__(kGenBlock) k_generate(WaveParams wp, WaveBuffe
     }
     if (inside && wp.max_depth > 0) {
       PathSampler s;
-      s.init(x + wp.film.width * y, wp.sample_base + slot / wp.film.slots_per_sample,
-             wp.film.width * wp.film.height, wp.seed);
+      s.init(x + wp.film.width * y, wp.sample_base + sample, wp.film.width * wp.film.height, wp.seed);
       // pixel jitter then lens sample (pt.cu:438-446); image x is flipped
       const float2 j = s.next2d();
       const float w = (float)wp.film.width, h = (float)wp.film.height;
@@ -174,9 +173,9 @@ __global__ void __launch_bounds__(kBlock) k_miss(WaveParams wp, SceneView sc, Wa
     const uint32_t slot = wb.class_queue[CLS_MISS][i];
     if (wp.single_launch) {
       // firsthit is already false once an earlier sample of the launch hit geometry (pt.cu:509)
-      uint32_t px, py;
-      slot_to_pixel(wp.film, slot % wp.film.slots_per_sample, px, py);
-      if (wp.sample_base + slot / wp.film.slots_per_sample > wb.first_hit[px + wp.film.width * py]) continue;
+      uint32_t px, py, sample;
+      slot_to_pixel(wp.film, slot, px, py, sample);
+      if (wp.sample_base + sample > wb.first_hit[px + wp.film.width * py]) continue;
     }
     const float3 d = f3(wb.ray_d[slot]);
     const float3 thr = f3(wb.thr[slot]);
@@ -215,9 +214,9 @@ __global__ void __launch_bounds__(kBlock, FRD_SHADE_BLOCKS) k_shade(WaveParams w
       ray_d = f3(rd);
       throughput = f3(thr4);
       const uint32_t face = __float_as_uint(hit.w);
-      uint32_t px, py;
-      slot_to_pixel(wp.film, slot % wp.film.slots_per_sample, px, py);
-      smp = restore_sampler(wp, slot, px, py, thr4.w);
+      uint32_t px, py, sample;
+      slot_to_pixel(wp.film, slot, px, py, sample);
+      smp = restore_sampler(wp, sample, px, py, thr4.w);
 
       // ---- surface (fill_surface_info, pt.cu:141-179) ----
       const uint3 idx = sc.indices[face];
@@ -454,9 +453,8 @@ __global__ void __launch_bounds__(256) k_first_hit(WaveParams wp, WaveBuffers wb
   if (x >= wp.film.width || y >= wp.film.height) return;
   const uint32_t pixel = x + wp.film.width * y;
   if (wb.first_hit[pixel] != 0xffffffffu) return;  // an earlier wave of this launch
-  const uint32_t slot0 = pixel_to_slot(wp.film, x, y);
   for (uint32_t s = 0; s < wp.n_samples; ++s) {
-    if (__float_as_uint(wb.hit[s * wp.film.slots_per_sample + slot0].w) != kNoHit) {
+    if (__float_as_uint(wb.hit[pixel_to_slot(wp.film, x, y, s)].w) != kNoHit) {
       wb.first_hit[pixel] = wp.sample_base + s;
       return;
     }
@@ -472,7 +470,6 @@ __global__ void __launch_bounds__(256) k_film(WaveParams wp, WaveBuffers wb, fre
   const uint32_t y = blockIdx.y * blockDim.y + threadIdx.y;
   if (x >= wp.film.width || y >= wp.film.height) return;
   const uint32_t pixel = x + wp.film.width * y;
-  const uint32_t slot0 = pixel_to_slot(wp.film, x, y);
 
   float3 beauty = f3(layers.beauty[pixel]);
   float3 position = layers.position ? f3(layers.position[pixel]) : f3(0.f);
@@ -487,7 +484,7 @@ __global__ void __launch_bounds__(256) k_film(WaveParams wp, WaveBuffers wb, fre
 
   uint32_t n_spp = wp.sample_base;
   for (uint32_t s = 0; s < wp.n_samples; ++s) {
-    const uint32_t slot = s * wp.film.slots_per_sample + slot0;
+    const uint32_t slot = pixel_to_slot(wp.film, x, y, s);
     const float4 L = wb.L[slot];
     float3 radiance = f3(L);
     if (bad3(radiance)) radiance = f3(0.f);  // pt.cu:475-478
@@ -678,7 +675,7 @@ void launch_wave_begin(cudaStream_t s, const WaveBuffers& wb, unsigned long long
 
 void launch_generate(cudaStream_t s, const WaveParams& wp, const WaveBuffers& wb)
 {
-  const uint32_t n_slots = wp.n_samples * wp.film.slots_per_sample;
+  const uint32_t n_slots = film_groups(wp.film, wp.n_samples) * wp.film.slots_per_group;
   k_generate<<<(n_slots + kGenBlock - 1) / kGenBlock, kGenBlock, 0, s>>>(wp, wb);
   FR_CUDA_LAUNCH_CHECK();
 }

@@ -47,7 +47,23 @@ struct AlphaTest {
   __shared__ uint2 s_stack[kSmemStack * kBlock]; \
   uint2* const stack_column = s_stack + threadIdx.x
 
+// Counting builds of the stages (set_traversal_counting): nodes visited / triangles tested per ray type,
+// summed over the retiring lanes (retire() runs with the warp converged) -- the measured N_node / N_tri of
+// the issue-slot roofline.  The timed path uses the COUNT = false instantiations.
+template <bool COUNT>
+FR_D void count_retire(WaveControl* ctl, int type, bool has, const TraceCounters& c)
+{
+  if (!COUNT) return;
+  const uint32_t nn = __reduce_add_sync(0xffffffffu, has ? c.nodes : 0u);
+  const uint32_t nt = __reduce_add_sync(0xffffffffu, has ? c.tris : 0u);
+  if (lane_id() == 0 && (nn | nt)) {
+    atomicAdd(&ctl->nodes[type], (unsigned long long)nn);
+    atomicAdd(&ctl->tris[type], (unsigned long long)nt);
+  }
+}
+
 // ---- radiance rays: closest hit, then "sort by material" ---------------------------------
+template <bool COUNT>
 struct ClosestPolicy {
   const SceneView& sc;
   const WaveBuffers& wb;
@@ -66,8 +82,9 @@ struct ClosestPolicy {
     tmin = 0.0f;
     tmax = 1e9f;
   }
-  FR_D void retire(bool has, const HitRecord& h, const TraceCounters&)
+  FR_D void retire(bool has, const HitRecord& h, const TraceCounters& cnt)
   {
+    count_retire<COUNT>(wb.ctl, 0, has, cnt);
     int cls = -1;
     if (has) {
       __stcs(&wb.hit[slot], make_float4(h.t, h.u, h.v, __uint_as_float(h.face)));
@@ -89,15 +106,17 @@ struct ClosestPolicy {
   }
 };
 
+template <bool COUNT>
 __global__ void __launch_bounds__(kBlock, FRD_TRACE_BLOCKS) k_trace_closest(SceneView sc, WaveBuffers wb, uint32_t depth, int refill, int tri_lanes,
                                                              const uint32_t* order)
 {
   FR_DECLARE_STACK();
-  ClosestPolicy pol{sc, wb, order ? order : wb.queue[depth & 1u], depth, 0u};
-  trace_queue<false, false>(sc.bvh, pol, &wb.ctl->cursor[0], wb.ctl->n[Q_CUR], stack_column, kBlock, refill, tri_lanes);
+  ClosestPolicy<COUNT> pol{sc, wb, order ? order : wb.queue[depth & 1u], depth, 0u};
+  trace_queue<false, COUNT>(sc.bvh, pol, &wb.ctl->cursor[0], wb.ctl->n[Q_CUR], stack_column, kBlock, refill, tri_lanes);
 }
 
 // ---- visibility rays: any hit; an unoccluded ray adds its contribution ----------------------
+template <bool COUNT>
 struct ShadowPolicy {
   const SceneView& sc;
   const WaveBuffers& wb;
@@ -117,8 +136,9 @@ struct ShadowPolicy {
     path = __float_as_uint(r1.w);
     c = f3(r2);
   }
-  FR_D void retire(bool has, const HitRecord& h, const TraceCounters&)
+  FR_D void retire(bool has, const HitRecord& h, const TraceCounters& cnt)
   {
+    count_retire<COUNT>(wb.ctl, 1, has, cnt);
     if (has && h.face == kNoHit) {
       // one ray per path and kernel: plain read-modify-write, deterministic order
       float4 L = wb.L[path];
@@ -130,18 +150,20 @@ struct ShadowPolicy {
   }
 };
 
+template <bool COUNT>
 __global__ void __launch_bounds__(kBlock, FRD_TRACE_BLOCKS) k_trace_shadow(SceneView sc, WaveBuffers wb, int which, int refill, int tri_lanes,
                                                             const uint32_t* order)
 {
   FR_DECLARE_STACK();
   // which == 3: the MIS-ray queue holding visibility records (scenes without emitters, shade.cu)
-  ShadowPolicy pol{sc, wb, reinterpret_cast<const float4*>(which < 3 ? wb.shadow[which] : (const ShadowRay*)wb.light), order,
+  ShadowPolicy<COUNT> pol{sc, wb, reinterpret_cast<const float4*>(which < 3 ? wb.shadow[which] : (const ShadowRay*)wb.light), order,
                    0u, f3(0.f)};
-  trace_queue<true, false>(sc.bvh, pol, &wb.ctl->cursor[2 + which], wb.ctl->n[Q_SHADOW0 + which], stack_column, kBlock,
+  trace_queue<true, COUNT>(sc.bvh, pol, &wb.ctl->cursor[2 + which], wb.ctl->n[Q_SHADOW0 + which], stack_column, kBlock,
                            refill, tri_lanes);
 }
 
 // ---- MIS rays: closest hit, emitter record + MIS weight in the epilogue -----------------------
+template <bool COUNT>
 struct LightPolicy {
   const SceneView& sc;
   const WaveBuffers& wb;
@@ -164,8 +186,9 @@ struct LightPolicy {
     w = f3(r2);
     cos_wi = r2.w;
   }
-  FR_D void retire(bool has, const HitRecord& h, const TraceCounters&)
+  FR_D void retire(bool has, const HitRecord& h, const TraceCounters& cnt)
   {
+    count_retire<COUNT>(wb.ctl, 2, has, cnt);
     if (!has) return;
     float3 le = f3(0.0f);
     float pdf_light = cos_wi / kPi;
@@ -209,12 +232,13 @@ struct LightPolicy {
 
 // (scenes without any emissive face never get here: their MIS rays are visibility rays with
 // the sky contribution precomputed by the shade stage, traced by k_trace_shadow)
+template <bool COUNT>
 __global__ void __launch_bounds__(kBlock, FRD_TRACE_BLOCKS) k_trace_light(SceneView sc, WaveBuffers wb, int refill, int tri_lanes,
                                                            const uint32_t* order)
 {
   FR_DECLARE_STACK();
-  LightPolicy pol{sc, wb, reinterpret_cast<const float4*>(wb.light), order, f3(0.f), f3(0.f), f3(0.f), 0.f, 0.f, 0u};
-  trace_queue<false, false>(sc.bvh, pol, &wb.ctl->cursor[5], wb.ctl->n[Q_LIGHT], stack_column, kBlock, refill, tri_lanes);
+  LightPolicy<COUNT> pol{sc, wb, reinterpret_cast<const float4*>(wb.light), order, f3(0.f), f3(0.f), f3(0.f), 0.f, 0.f, 0u};
+  trace_queue<false, COUNT>(sc.bvh, pol, &wb.ctl->cursor[5], wb.ctl->n[Q_LIGHT], stack_column, kBlock, refill, tri_lanes);
 }
 
 // stand-alone batch query for the parity tests: same driver and phases as the stages above
@@ -305,18 +329,27 @@ int persistent_grid(const void* kernel, int block)
 
 }  // namespace
 
+bool g_count_traversal = false;
+void set_traversal_counting(bool on) { g_count_traversal = on; }
+
 void launch_trace_closest(cudaStream_t s, const SceneView& sc, const WaveBuffers& wb, uint32_t depth,
                           const uint32_t* order)
 {
-  if (!g_grid_closest) g_grid_closest = persistent_grid(reinterpret_cast<const void*>(k_trace_closest), kBlock);
-  k_trace_closest<<<g_grid_closest, kBlock, 0, s>>>(sc, wb, depth, refill_lanes(), tri_lanes_closest(), order);
+  if (!g_grid_closest) g_grid_closest = persistent_grid(reinterpret_cast<const void*>(k_trace_closest<false>), kBlock);
+  if (g_count_traversal)
+    k_trace_closest<true><<<g_grid_closest, kBlock, 0, s>>>(sc, wb, depth, refill_lanes(), tri_lanes_closest(), order);
+  else
+    k_trace_closest<false><<<g_grid_closest, kBlock, 0, s>>>(sc, wb, depth, refill_lanes(), tri_lanes_closest(), order);
   FR_CUDA_LAUNCH_CHECK();
 }
 
 void launch_trace_shadow(cudaStream_t s, const SceneView& sc, const WaveBuffers& wb, int which, const uint32_t* order)
 {
-  if (!g_grid_shadow) g_grid_shadow = persistent_grid(reinterpret_cast<const void*>(k_trace_shadow), kBlock);
-  k_trace_shadow<<<g_grid_shadow, kBlock, 0, s>>>(sc, wb, which, refill_lanes(), tri_lanes_any(), order);
+  if (!g_grid_shadow) g_grid_shadow = persistent_grid(reinterpret_cast<const void*>(k_trace_shadow<false>), kBlock);
+  if (g_count_traversal)
+    k_trace_shadow<true><<<g_grid_shadow, kBlock, 0, s>>>(sc, wb, which, refill_lanes(), tri_lanes_any(), order);
+  else
+    k_trace_shadow<false><<<g_grid_shadow, kBlock, 0, s>>>(sc, wb, which, refill_lanes(), tri_lanes_any(), order);
   FR_CUDA_LAUNCH_CHECK();
 }
 
@@ -326,8 +359,11 @@ void launch_trace_light(cudaStream_t s, const SceneView& sc, const WaveBuffers& 
     launch_trace_shadow(s, sc, wb, 3, order);
     return;
   }
-  if (!g_grid_light) g_grid_light = persistent_grid(reinterpret_cast<const void*>(k_trace_light), kBlock);
-  k_trace_light<<<g_grid_light, kBlock, 0, s>>>(sc, wb, refill_lanes(), tri_lanes_closest(), order);
+  if (!g_grid_light) g_grid_light = persistent_grid(reinterpret_cast<const void*>(k_trace_light<false>), kBlock);
+  if (g_count_traversal)
+    k_trace_light<true><<<g_grid_light, kBlock, 0, s>>>(sc, wb, refill_lanes(), tri_lanes_closest(), order);
+  else
+    k_trace_light<false><<<g_grid_light, kBlock, 0, s>>>(sc, wb, refill_lanes(), tri_lanes_closest(), order);
   FR_CUDA_LAUNCH_CHECK();
 }
 

@@ -101,7 +101,7 @@ struct WaveControl {
   uint32_t n_class[CLS_COUNT];
   uint32_t cursor_class[CLS_COUNT];
   unsigned long long rays_closest, rays_shadow, rays_light;  // traced rays
-  unsigned long long nodes_visited, tris_tested;             // only in stats builds
+  unsigned long long nodes[3], tris[3];  // counting builds only: per ray type (closest, shadow, MIS)
   unsigned long long paths;
 };
 
@@ -126,34 +126,62 @@ struct WaveBuffers {
   float4* pix_aov2;
 };
 
-// image <-> path slot mapping: pixels are walked in 8x4 tiles so that one warp owns
-// a compact screen tile (coherent primary rays).
+// image <-> path slot mapping.  A warp owns 32 consecutive path slots = a small pixel block times
+// `spw` consecutive samples of it (spw = 2^spw_log2 samples per warp, block = 32 / spw pixels):
+//   spw  1: 8x4 pixels x 1 sample     spw  8: 2x2 pixels x  8 samples
+//   spw  2: 4x4 pixels x 2 samples    spw 16: 2x1 pixels x 16 samples
+//   spw  4: 4x2 pixels x 4 samples    spw 32: 1   pixel  x 32 samples
+// Camera rays (and the first-bounce sun rays) of one warp then form a beam about one pixel wide:
+// their traversals take the same decisions, so the per-lane state machines of trace_queue() stay in
+// lock step (node and triangle phases run with most lanes active).  The samples of a wave are
+// handed out in groups of spw; the slots of a group beyond n_samples stay empty.
 struct FilmGeom {
   uint32_t width, height;
   uint32_t tiles_x, tiles_y;
-  uint32_t slots_per_sample;  // tiles_x * tiles_y * 32
+  uint32_t slots_per_group;  // tiles_x * tiles_y * 32: one group = spw samples of every pixel
+  uint32_t spw_log2;         // log2(samples per warp)
+  uint32_t bw_log2, bh_log2;  // log2 of the pixel block a warp covers
 };
 
-__host__ __device__ inline FilmGeom make_film_geom(uint32_t w, uint32_t h)
+__host__ __device__ inline FilmGeom make_film_geom(uint32_t w, uint32_t h, uint32_t spw_log2 = 0)
 {
   FilmGeom g;
   g.width = w;
   g.height = h;
-  g.tiles_x = (w + 7) / 8;
-  g.tiles_y = (h + 3) / 4;
-  g.slots_per_sample = g.tiles_x * g.tiles_y * 32u;
+  g.spw_log2 = spw_log2 > 5u ? 5u : spw_log2;
+  const uint32_t pix_log2 = 5u - g.spw_log2;  // pixels per warp: 8x4, 4x4, 4x2, 2x2, 2x1, 1x1
+  g.bw_log2 = (pix_log2 + 1u) >> 1;
+  g.bh_log2 = pix_log2 >> 1;
+  g.tiles_x = (w + (1u << g.bw_log2) - 1u) >> g.bw_log2;
+  g.tiles_y = (h + (1u << g.bh_log2) - 1u) >> g.bh_log2;
+  g.slots_per_group = g.tiles_x * g.tiles_y * 32u;
   return g;
 }
-__host__ __device__ inline bool slot_to_pixel(const FilmGeom& g, uint32_t slot_in_sample, uint32_t& x, uint32_t& y)
+// sample groups (of spw samples) needed for n samples, and the slots they occupy
+__host__ __device__ inline uint32_t film_groups(const FilmGeom& g, uint32_t n_samples)
 {
-  const uint32_t tile = slot_in_sample >> 5, lane = slot_in_sample & 31u;
-  x = (tile % g.tiles_x) * 8u + (lane & 7u);
-  y = (tile / g.tiles_x) * 4u + (lane >> 3);
+  return (n_samples + (1u << g.spw_log2) - 1u) >> g.spw_log2;
+}
+// slot -> pixel and sample index within the wave; false if the slot lies outside the image
+__host__ __device__ inline bool slot_to_pixel(const FilmGeom& g, uint32_t slot, uint32_t& x, uint32_t& y, uint32_t& s)
+{
+  const uint32_t group = slot / g.slots_per_group, rem = slot - group * g.slots_per_group;
+  const uint32_t tile = rem >> 5, lane = rem & 31u;
+  const uint32_t pix_log2 = 5u - g.spw_log2;
+  const uint32_t p = lane & ((1u << pix_log2) - 1u);
+  s = (group << g.spw_log2) + (lane >> pix_log2);
+  const uint32_t ty = tile / g.tiles_x, tx = tile - ty * g.tiles_x;
+  x = (tx << g.bw_log2) + (p & ((1u << g.bw_log2) - 1u));
+  y = (ty << g.bh_log2) + (p >> g.bw_log2);
   return x < g.width && y < g.height;
 }
-__host__ __device__ inline uint32_t pixel_to_slot(const FilmGeom& g, uint32_t x, uint32_t y)
+__host__ __device__ inline uint32_t pixel_to_slot(const FilmGeom& g, uint32_t x, uint32_t y, uint32_t s)
 {
-  return ((y >> 2) * g.tiles_x + (x >> 3)) * 32u + ((y & 3u) << 3) + (x & 7u);
+  const uint32_t pix_log2 = 5u - g.spw_log2;
+  const uint32_t group = s >> g.spw_log2, s_in = s & ((1u << g.spw_log2) - 1u);
+  const uint32_t tile = (y >> g.bh_log2) * g.tiles_x + (x >> g.bw_log2);
+  const uint32_t p = ((y & ((1u << g.bh_log2) - 1u)) << g.bw_log2) | (x & ((1u << g.bw_log2) - 1u));
+  return group * g.slots_per_group + tile * 32u + (s_in << pix_log2) + p;
 }
 
 // Coherence sort (sort.cu): which queue, and the grid the ray origins are binned on.

@@ -32,6 +32,9 @@ void launch_trace_closest(cudaStream_t s, const SceneView& sc, const WaveBuffers
 void launch_trace_shadow(cudaStream_t s, const SceneView& sc, const WaveBuffers& wb, int which,
                          const uint32_t* order = nullptr);
 void launch_trace_light(cudaStream_t s, const SceneView& sc, const WaveBuffers& wb, const uint32_t* order = nullptr);
+// counting instantiations of the three stages: nodes visited / triangles tested go to WaveControl::nodes / tris
+// (measurement only; process-wide switch)
+void set_traversal_counting(bool on);
 
 // sort.cu: counting sort of queue `which` (SortQueue) by origin cell + direction octant.
 // keys: [queue size] scratch, bins: [sort_bins(g)] scratch, out: [queue size] sorted order

@@ -42,6 +42,9 @@ def reduce_film(dist, sums, total_spp, dst=0):
         if dist.get_rank() != dst:
             return sums
     sums.mul_(1.0 / float(total_spp))
+    if sums.dim() >= 1 and sums.shape[-1] == 4:
+        # every rank's film wrote alpha = 1, so the reduced alpha is world / total_spp: reset it (k_scale_layers does the same)
+        sums[..., 3] = 1.0
     return sums
 
 

@@ -41,6 +41,10 @@ struct RenderStatistics {
   unsigned long long rays_shadow = 0;
   unsigned long long rays_light = 0;
   unsigned long long kernel_launches = 0;
+  // only filled while set_traversal_counting(true): BVH nodes visited / triangles tested by the
+  // radiance, shadow and MIS rays (index 0, 1, 2)
+  unsigned long long nodes_visited[3] = {0, 0, 0};
+  unsigned long long tris_tested[3] = {0, 0, 0};
   unsigned long long total_rays() const { return rays_radiance + rays_shadow + rays_light; }
 };
 
@@ -107,6 +111,10 @@ class Renderer
   // first-hit AOVs outlive the sample loop (pt.cu:432-433, 744-759) -- what app/rtcamp8.cpp produces.  Off by
   // default: render(n_samples) equals n_samples launches of one sample, what the reference GUI produces.
   void set_single_launch(bool on);
+  // samples of one pixel block that share a warp (1, 2, 4, 8, 16, 32): a scheduling choice, no sample changes
+  void set_samples_per_warp(uint32_t spw);
+  // measurement: run the counting instantiations of the traversal kernels (process-wide switch)
+  void set_traversal_counting(bool on);
   // per-stage device time, measured with CUDA events on the renderer's stream;
   // stages: generate, trace_closest, shade, trace_shadow, trace_light, advance, film
   static constexpr int kStageCount = 7;

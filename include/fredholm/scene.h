@@ -103,6 +103,10 @@ struct Scene {
   Scene() = default;
 
   bool is_valid() const;
+  // extension: full consistency check of the arrays the renderer indexes on the device (array lengths, vertex /
+  // material / instance / texture indices, sub-meshes tiling the face range); throws std::runtime_error
+  // "invalid scene: ..." -- Renderer::load_scene / set_scene call it before uploading
+  void validate() const;
   void clear();
 
   // .obj or .gltf by extension; throws std::runtime_error otherwise

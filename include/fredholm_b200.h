@@ -88,6 +88,15 @@ typedef struct fr_scene fr_scene;
 fr_scene* fr_scene_create(void);
 void fr_scene_destroy(fr_scene* s);
 int fr_scene_load(fr_scene* s, const char* path, int clear);
+/* fills the flat arrays of Scene (scene.h:107-130) directly; layout as fr_set_scene_arrays */
+int fr_scene_set_arrays(fr_scene* s, const float* vertices, const float* normals, const float* texcoords,
+                        uint32_t n_vertices, const uint32_t* indices, const uint32_t* material_ids,
+                        const uint32_t* instance_ids, uint32_t n_faces, const void* materials /* 180 B each */,
+                        uint32_t n_materials, const uint32_t* submesh_offsets, const uint32_t* submesh_n_faces,
+                        const float* transforms, uint32_t n_submeshes);
+/* Scene::validate (extension): every index the device code follows is in range, sub-meshes tile the faces;
+ * fails with "invalid scene: ..." -- the check every upload (fr_set_scene*, fr_load_scene) runs first */
+int fr_scene_validate(const fr_scene* s);
 int fr_scene_get_sizes(fr_scene* s, uint32_t* out6);
 int fr_scene_get_arrays(fr_scene* s, float* vertices, float* normals, float* texcoords, uint32_t* indices,
                         uint32_t* material_ids, uint32_t* instance_ids, void* materials, uint32_t* submesh_offsets,
@@ -136,6 +145,12 @@ int fr_scale_layers(fr_renderer* r, const fr_layers* layers_dev, float scale);
 /* out5 = paths, radiance rays, shadow rays, light rays, kernel launches */
 int fr_get_statistics(fr_renderer* r, uint64_t* out5);
 int fr_reset_statistics(fr_renderer* r);
+/* measurement: counting instantiations of the traversal kernels (process-wide switch); out6 = CWBVH nodes
+ * visited by radiance / shadow / MIS rays, then triangles tested by the same three, since the last reset */
+int fr_set_traversal_counting(fr_renderer* r, int on);
+int fr_get_traversal_counters(fr_renderer* r, uint64_t* out6);
+/* samples of one pixel block that share a warp (1, 2, 4, 8, 16, 32; csrc/wavefront.h FilmGeom) */
+int fr_set_samples_per_warp(fr_renderer* r, uint32_t spw);
 /* per-stage device time from CUDA events on the renderer's stream; 7 stages:
  * generate, trace_closest, shade, trace_shadow, trace_light, advance, film.
  * fr_get_stage_times synchronises, returns the accumulated ms / launch counts and clears them */
