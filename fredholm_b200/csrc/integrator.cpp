@@ -249,7 +249,7 @@ void Integrator::render(const SceneView& scene, const fredholm::CameraParams& ca
         if (class_mask & (1u << c)) stage(STAGE_SHADE, [&] { launch_shade(m_stream, wp, scene, wb, depth, c); });
       if (scene.has_dir_light) {
         sort_queue(2u, SORT_SHADOW0, false);  // all sun rays point the same way
-        stage(STAGE_TRACE_SHADOW, [&] { launch_trace_shadow(m_stream, scene, wb, 0, order); });
+        stage(STAGE_TRACE_SHADOW, [&] { launch_trace_shadow(m_stream, scene, wb, 0, order, depth == 0); });
       }
       sort_queue(4u, SORT_SHADOW1, true);
       stage(STAGE_TRACE_SHADOW, [&] { launch_trace_shadow(m_stream, scene, wb, 1, order); });

@@ -306,6 +306,12 @@ int refill_lanes()
   static const int v = env_int("FRD_REFILL_LANES", 8);
   return v;
 }
+// the same threshold for launches whose queue is in beam order (camera rays, first-bounce sun rays)
+int refill_lanes_coherent()
+{
+  static const int v = env_int("FRD_REFILL_LANES_COHERENT", refill_lanes());
+  return v;
+}
 // lanes with a pending triangle that trigger a triangle phase (closest-hit / any-hit kernels)
 int tri_lanes_closest()
 {
@@ -336,27 +342,30 @@ void launch_trace_closest(cudaStream_t s, const SceneView& sc, const WaveBuffers
                           const uint32_t* order)
 {
   if (!g_grid_closest) g_grid_closest = persistent_grid(reinterpret_cast<const void*>(k_trace_closest<false>), kBlock);
+  const int refill = depth == 0 ? refill_lanes_coherent() : refill_lanes();
   if (g_count_traversal)
-    k_trace_closest<true><<<g_grid_closest, kBlock, 0, s>>>(sc, wb, depth, refill_lanes(), tri_lanes_closest(), order);
+    k_trace_closest<true><<<g_grid_closest, kBlock, 0, s>>>(sc, wb, depth, refill, tri_lanes_closest(), order);
   else
-    k_trace_closest<false><<<g_grid_closest, kBlock, 0, s>>>(sc, wb, depth, refill_lanes(), tri_lanes_closest(), order);
+    k_trace_closest<false><<<g_grid_closest, kBlock, 0, s>>>(sc, wb, depth, refill, tri_lanes_closest(), order);
   FR_CUDA_LAUNCH_CHECK();
 }
 
-void launch_trace_shadow(cudaStream_t s, const SceneView& sc, const WaveBuffers& wb, int which, const uint32_t* order)
+void launch_trace_shadow(cudaStream_t s, const SceneView& sc, const WaveBuffers& wb, int which, const uint32_t* order,
+                         bool coherent)
 {
   if (!g_grid_shadow) g_grid_shadow = persistent_grid(reinterpret_cast<const void*>(k_trace_shadow<false>), kBlock);
+  const int refill = coherent ? refill_lanes_coherent() : refill_lanes();
   if (g_count_traversal)
-    k_trace_shadow<true><<<g_grid_shadow, kBlock, 0, s>>>(sc, wb, which, refill_lanes(), tri_lanes_any(), order);
+    k_trace_shadow<true><<<g_grid_shadow, kBlock, 0, s>>>(sc, wb, which, refill, tri_lanes_any(), order);
   else
-    k_trace_shadow<false><<<g_grid_shadow, kBlock, 0, s>>>(sc, wb, which, refill_lanes(), tri_lanes_any(), order);
+    k_trace_shadow<false><<<g_grid_shadow, kBlock, 0, s>>>(sc, wb, which, refill, tri_lanes_any(), order);
   FR_CUDA_LAUNCH_CHECK();
 }
 
 void launch_trace_light(cudaStream_t s, const SceneView& sc, const WaveBuffers& wb, const uint32_t* order)
 {
   if (sc.n_lights == 0) {
-    launch_trace_shadow(s, sc, wb, 3, order);
+    launch_trace_shadow(s, sc, wb, 3, order, false);
     return;
   }
   if (!g_grid_light) g_grid_light = persistent_grid(reinterpret_cast<const void*>(k_trace_light<false>), kBlock);

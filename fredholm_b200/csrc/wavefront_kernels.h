@@ -29,8 +29,9 @@ void launch_scale_layers(cudaStream_t s, const fredholm::RenderLayer& layers, ui
 // for the radiance queue it holds path slots, for the record queues item indices
 void launch_trace_closest(cudaStream_t s, const SceneView& sc, const WaveBuffers& wb, uint32_t depth,
                           const uint32_t* order = nullptr);
+// coherent: the queue is in beam order (first-bounce sun rays), see FRD_REFILL_LANES_COHERENT
 void launch_trace_shadow(cudaStream_t s, const SceneView& sc, const WaveBuffers& wb, int which,
-                         const uint32_t* order = nullptr);
+                         const uint32_t* order = nullptr, bool coherent = false);
 void launch_trace_light(cudaStream_t s, const SceneView& sc, const WaveBuffers& wb, const uint32_t* order = nullptr);
 // counting instantiations of the three stages: nodes visited / triangles tested go to WaveControl::nodes / tris
 // (measurement only; process-wide switch)
