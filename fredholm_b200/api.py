@@ -111,6 +111,21 @@ SIGNATURES = {
     "fr_render_frame_host": (C.c_int, [_vp, _fp, C.c_float, C.c_float, C.c_float, _fp, C.POINTER(_Layers),
                                        C.c_uint32, C.c_uint32]),
     "fr_scale_layers": (C.c_int, [_vp, C.POINTER(_Layers), C.c_float]),
+    "fr_get_device_attributes": (C.c_int, [C.c_int, _up, _u64p]),
+    "fr_comm_get_unique_id": (C.c_int, [_u8p]),
+    "fr_comm_init": (C.c_int, [_vp, _u8p, C.c_int, C.c_int]),
+    "fr_comm_destroy": (C.c_int, [_vp]),
+    "fr_sample_slice": (C.c_int, [C.c_uint32, C.c_int, C.c_int, _up, _up]),
+    "fr_render_sharded": (C.c_int, [_vp, _fp, C.c_float, C.c_float, C.c_float, _fp, C.POINTER(_Layers), C.c_uint32,
+                                    C.c_uint32, C.c_int]),
+    "fr_reduce_layers": (C.c_int, [_vp, C.POINTER(_Layers), C.c_uint32, C.c_int]),
+    "fr_multi_create": (_vp, [C.POINTER(C.c_int), C.c_int]),
+    "fr_multi_destroy": (None, [_vp]),
+    "fr_multi_size": (C.c_int, [_vp]),
+    "fr_multi_renderer": (_vp, [_vp, C.c_int]),
+    "fr_multi_render": (C.c_int, [_vp, _fp, C.c_float, C.c_float, C.c_float, _fp, C.POINTER(_Layers), C.c_uint32,
+                                  C.c_uint32]),
+    "fr_multi_wait": (C.c_int, [_vp]),
     "fr_get_statistics": (C.c_int, [_vp, _u64p]),
     "fr_reset_statistics": (C.c_int, [_vp]),
     "fr_set_traversal_counting": (C.c_int, [_vp, C.c_int]),
@@ -405,12 +420,53 @@ class Renderer:
         self._h = L.fr_renderer_create(device)
         if not self._h:
             raise FredholmError(L.fr_last_error().decode())
+        self._borrowed = False
         self.width = self.height = 0
+
+    @classmethod
+    def _view(cls, handle):
+        """Wraps a handle owned by someone else (a rank of a MultiRenderer); close() leaves it alone."""
+        r = cls.__new__(cls)
+        r._h = handle
+        r._borrowed = True
+        r.width = r.height = 0
+        return r
 
     def close(self):
         if getattr(self, "_h", None):
-            lib().fr_renderer_destroy(self._h)
+            if not getattr(self, "_borrowed", False):
+                lib().fr_renderer_destroy(self._h)
             self._h = None
+
+    # ---- multi-GPU: this renderer as one rank of a world (include/fredholm/multi_gpu.h) ----
+    def comm_init(self, comm_id, rank, world):
+        """Collective: ncclCommInitRank inside the C++ core.  comm_id: the 128 bytes of comm_unique_id() made on
+        rank 0 and shipped to every rank."""
+        ident = np.frombuffer(bytes(comm_id), dtype=np.uint8).copy()
+        assert ident.size == 128
+        _check(lib().fr_comm_init(self._h, ident.ctypes.data_as(_u8p), int(rank), int(world)))
+
+    def comm_destroy(self):
+        _check(lib().fr_comm_destroy(self._h))
+
+    def _layers_struct(self, layers):
+        if isinstance(layers, DeviceLayers):
+            return layers.struct()
+        st = _Layers()
+        for name in LAYER_NAMES:
+            setattr(st, name, layers.get(name))
+        return st
+
+    def render_sharded(self, camera, bg_color, layers, total_spp, max_depth, root=0):
+        """Collective: this rank's sample slice of a total_spp frame (sums into the ZEROED layers), one ncclReduce of
+        the bound layers onto root, division by total_spp there.  Asynchronous on the renderer's stream."""
+        st = self._layers_struct(layers)
+        _check(lib().fr_render_sharded(self._h, _f(_f32(camera.transform, 12)), camera.fov, camera.F, camera.focus,
+                                       _f(_f32(bg_color, 3)), C.byref(st), int(total_spp), int(max_depth), int(root)))
+
+    def reduce_layers(self, layers, total_spp, root=0):
+        st = self._layers_struct(layers)
+        _check(lib().fr_reduce_layers(self._h, C.byref(st), int(total_spp), int(root)))
 
     def __del__(self):
         try:
@@ -603,10 +659,10 @@ class Renderer:
         _check(lib().fr_scale_layers(self._h, C.byref(st), float(scale)))
 
     def statistics(self):
-        out = np.zeros(5, np.uint64)
+        out = np.zeros(6, np.uint64)
         _check(lib().fr_get_statistics(self._h, out.ctypes.data_as(_u64p)))
         d = dict(paths=int(out[0]), rays_radiance=int(out[1]), rays_shadow=int(out[2]), rays_light=int(out[3]),
-                 kernel_launches=int(out[4]))
+                 kernel_launches=int(out[4]), rays_skipped=int(out[5]))
         d["rays"] = d["rays_radiance"] + d["rays_shadow"] + d["rays_light"]
         return d
 
@@ -668,6 +724,72 @@ class Renderer:
         out = np.zeros_like(d)
         _check(lib().fr_sky_radiance(self._h, _f(d), len(d), _f(out)))
         return out
+
+
+def device_attributes(device=0):
+    out = np.zeros(4, np.uint32)
+    mem = np.zeros(1, np.uint64)
+    _check(lib().fr_get_device_attributes(int(device), _u(out), mem.ctypes.data_as(_u64p)))
+    return dict(sm_count=int(out[0]), clock_khz=int(out[1]), cc=int(out[2]), l2_bytes=int(out[3]), total_mem=int(mem[0]))
+
+
+def comm_unique_id():
+    """ncclGetUniqueId through the C ABI: 128 bytes, made on rank 0."""
+    out = np.zeros(128, np.uint8)
+    _check(lib().fr_comm_get_unique_id(out.ctypes.data_as(_u8p)))
+    return out.tobytes()
+
+
+def sample_slice(total_spp, rank, world):
+    """(first, count) of rank's sample slice -- the C++ core's rule (whole 16-sample CMJ patterns)."""
+    first, count = C.c_uint32(), C.c_uint32()
+    _check(lib().fr_sample_slice(int(total_spp), int(rank), int(world), C.byref(first), C.byref(count)))
+    return first.value, count.value
+
+
+class MultiRenderer:
+    """fredholm::MultiGpuRenderer: one process, one renderer + host thread per device, NCCL inside the core."""
+
+    def __init__(self, devices=None):
+        L = lib()
+        if L.fr_device_count() <= 0:
+            raise FredholmError("no CUDA device (fredholm_b200 has no CPU fallback)")
+        if devices:
+            arr = (C.c_int * len(devices))(*devices)
+            self._h = L.fr_multi_create(arr, len(devices))
+        else:
+            self._h = L.fr_multi_create(None, 0)
+        if not self._h:
+            raise FredholmError(L.fr_last_error().decode())
+        self.ranks = [Renderer._view(L.fr_multi_renderer(self._h, i)) for i in range(L.fr_multi_size(self._h))]
+
+    def __len__(self):
+        return len(self.ranks)
+
+    def for_each(self, f):
+        for r in self.ranks:
+            f(r)
+
+    def render(self, camera, bg_color, layers_rank0, total_spp, max_depth):
+        st = self.ranks[0]._layers_struct(layers_rank0)
+        _check(lib().fr_multi_render(self._h, _f(_f32(camera.transform, 12)), camera.fov, camera.F, camera.focus,
+                                     _f(_f32(bg_color, 3)), C.byref(st), int(total_spp), int(max_depth)))
+
+    def wait(self):
+        _check(lib().fr_multi_wait(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            for r in self.ranks:
+                r.close()
+            lib().fr_multi_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def sampler_sequence(width, height, seed, image_idx, n_spp, kinds):

@@ -9,18 +9,22 @@
 
 #include "fredholm/batch.h"
 #include "fredholm/denoiser.h"
+#include "fredholm/multi_gpu.h"
 #include "kernels/post-process.h"
 #include "renderer_impl.h"
 
 using namespace fredholm;
 
 struct fr_renderer {
-  Renderer renderer;
+  std::unique_ptr<Renderer> owned;  // null for the per-rank views of an fr_multi
+  Renderer& renderer;
+  std::unique_ptr<ShardedRenderer> rank;  // fr_comm_init: this renderer is one rank of a multi-GPU world
   std::vector<Texture> staged_textures;
   // device layers owned by fr_render_frame_host
   frd::DevBuf<float4> h_beauty, h_position, h_normal, h_texcoord, h_albedo;
   frd::DevBuf<float> h_depth;
-  explicit fr_renderer(int dev) : renderer(dev) {}
+  explicit fr_renderer(int dev) : owned(new Renderer(dev)), renderer(*owned) {}
+  explicit fr_renderer(Renderer& external) : renderer(external) {}
 };
 
 struct fr_scene {
@@ -448,20 +452,123 @@ int fr_render_frame_host(fr_renderer* r, const float* camera_transform12, float 
   });
 }
 
+// ---- multi-GPU (include/fredholm/multi_gpu.h) ----
+int fr_comm_get_unique_id(uint8_t* out128)
+{
+  return guarded([&] {
+    const CommId id = make_comm_id();
+    std::memcpy(out128, id.bytes, sizeof(id.bytes));
+  });
+}
+int fr_comm_init(fr_renderer* r, const uint8_t* id128, int rank, int world)
+{
+  return guarded([&] {
+    CommId id;
+    std::memcpy(id.bytes, id128, sizeof(id.bytes));
+    r->rank.reset();
+    r->rank = std::make_unique<ShardedRenderer>(r->renderer, id, rank, world);
+  });
+}
+int fr_comm_destroy(fr_renderer* r)
+{
+  return guarded([&] { r->rank.reset(); });
+}
+int fr_sample_slice(uint32_t total_spp, int rank, int world, uint32_t* first, uint32_t* count)
+{
+  return guarded([&] { sample_slice(total_spp, rank, world, *first, *count); });
+}
+int fr_render_sharded(fr_renderer* r, const float* camera_transform12, float fov, float F, float focus,
+                      const float* bg, const fr_layers* layers_dev, uint32_t total_spp, uint32_t max_depth, int root)
+{
+  return guarded([&] {
+    if (!r->rank) throw std::runtime_error("fr_render_sharded: call fr_comm_init first");
+    r->rank->render(make_camera(camera_transform12, fov, F, focus), make_float3(bg[0], bg[1], bg[2]),
+                    make_layers(layers_dev), total_spp, max_depth, root);
+  });
+}
+int fr_reduce_layers(fr_renderer* r, const fr_layers* layers_dev, uint32_t total_spp, int root)
+{
+  return guarded([&] {
+    if (!r->rank) throw std::runtime_error("fr_reduce_layers: call fr_comm_init first");
+    r->rank->reduce(make_layers(layers_dev), total_spp, root);
+  });
+}
+
+struct fr_multi {
+  MultiGpuRenderer multi;
+  std::vector<std::unique_ptr<fr_renderer>> views;  // per-rank handles for the fr_* scene / light / film calls
+  explicit fr_multi(const std::vector<int>& devs) : multi(devs)
+  {
+    for (int i = 0; i < multi.size(); ++i) views.emplace_back(new fr_renderer(multi.renderer(i)));
+  }
+};
+fr_multi* fr_multi_create(const int* devices, int n_devices)
+{
+  fr_multi* m = nullptr;
+  if (guarded([&] {
+        std::vector<int> devs;
+        if (devices && n_devices > 0) devs.assign(devices, devices + n_devices);
+        m = new fr_multi(devs);
+      }) != 0)
+    return nullptr;
+  return m;
+}
+void fr_multi_destroy(fr_multi* m)
+{
+  guarded([&] { delete m; });
+}
+int fr_multi_size(fr_multi* m) { return m ? m->multi.size() : 0; }
+fr_renderer* fr_multi_renderer(fr_multi* m, int rank)
+{
+  if (!m || rank < 0 || rank >= (int)m->views.size()) {
+    g_error = "fr_multi_renderer: rank outside the world";
+    return nullptr;
+  }
+  return m->views[rank].get();
+}
+int fr_multi_render(fr_multi* m, const float* camera_transform12, float fov, float F, float focus, const float* bg,
+                    const fr_layers* layers_dev_rank0, uint32_t total_spp, uint32_t max_depth)
+{
+  return guarded([&] {
+    m->multi.render(make_camera(camera_transform12, fov, F, focus), make_float3(bg[0], bg[1], bg[2]),
+                    make_layers(layers_dev_rank0), total_spp, max_depth);
+  });
+}
+int fr_multi_wait(fr_multi* m)
+{
+  return guarded([&] { m->multi.wait_for_completion(); });
+}
+
+int fr_get_device_attributes(int device, uint32_t* out4, uint64_t* total_mem)
+{
+  return guarded([&] {
+    cudaDeviceProp p;
+    FR_CUDA_CHECK(cudaGetDeviceProperties(&p, device));
+    int clock_khz = 0;
+    FR_CUDA_CHECK(cudaDeviceGetAttribute(&clock_khz, cudaDevAttrClockRate, device));
+    out4[0] = (uint32_t)p.multiProcessorCount;
+    out4[1] = (uint32_t)clock_khz;
+    out4[2] = (uint32_t)p.major * 10u + (uint32_t)p.minor;
+    out4[3] = (uint32_t)p.l2CacheSize;
+    if (total_mem) *total_mem = (uint64_t)p.totalGlobalMem;
+  });
+}
+
 int fr_scale_layers(fr_renderer* r, const fr_layers* layers_dev, float scale)
 {
   return guarded([&] { r->renderer.scale_layers(make_layers(layers_dev), scale); });
 }
 
-int fr_get_statistics(fr_renderer* r, uint64_t* out5)
+int fr_get_statistics(fr_renderer* r, uint64_t* out6)
 {
   return guarded([&] {
     const RenderStatistics s = r->renderer.get_statistics();
-    out5[0] = s.paths;
-    out5[1] = s.rays_radiance;
-    out5[2] = s.rays_shadow;
-    out5[3] = s.rays_light;
-    out5[4] = s.kernel_launches;
+    out6[0] = s.paths;
+    out6[1] = s.rays_radiance;
+    out6[2] = s.rays_shadow;
+    out6[3] = s.rays_light;
+    out6[4] = s.kernel_launches;
+    out6[5] = s.rays_skipped;
   });
 }
 int fr_set_traversal_counting(fr_renderer* r, int on)

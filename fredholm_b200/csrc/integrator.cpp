@@ -1,6 +1,9 @@
 #include "integrator.h"
 
+#include "nvtx.h"
+
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 
 namespace frd
@@ -74,9 +77,16 @@ cudaEvent_t Integrator::get_event()
   return e;
 }
 
+namespace
+{
+const char* const kStageNames[STAGE_COUNT] = {"generate", "trace_closest", "shade", "trace_shadow",
+                                              "trace_light", "advance", "film"};
+}
+
 template <typename F>
 void Integrator::stage(int id, F&& launch)
 {
+  FR_NVTX_RANGE(kStageNames[id]);
   if (!m_time_stages) {
     launch();
   } else {
@@ -220,7 +230,9 @@ void Integrator::render(const SceneView& scene, const fredholm::CameraParams& ca
     wb.pix_aov2 = m_pix_aov[2].get();
   }
 
+  FR_NVTX_RANGE("render");
   for (uint32_t done = 0; done < n_samples; done += per_wave) {
+    FR_NVTX_RANGE("wave");
     WaveParams wp;
     wp.film = film;
     wp.n_samples = std::min(per_wave, n_samples - done);
@@ -234,6 +246,11 @@ void Integrator::render(const SceneView& scene, const fredholm::CameraParams& ca
     stage(STAGE_ADVANCE, [&] { launch_wave_begin(m_stream, wb, (unsigned long long)wp.n_samples * width * height); });
     stage(STAGE_GENERATE, [&] { launch_generate(m_stream, wp, wb); });
     for (uint32_t depth = 0; depth < max_depth; ++depth) {
+#if FR_HAVE_NVTX
+      char bounce_name[24];
+      snprintf(bounce_name, sizeof(bounce_name), "bounce %u", depth);
+      FR_NVTX_RANGE(bounce_name);
+#endif
       // coherence sort (queue management, booked under "advance"): each queue is sorted right
       // before it is traced, so one scratch order buffer serves all of them
       const uint32_t* order = nullptr;
@@ -283,6 +300,7 @@ RenderStats Integrator::stats()
   s.rays_closest = h.rays_closest;
   s.rays_shadow = h.rays_shadow;
   s.rays_light = h.rays_light;
+  s.rays_skipped = h.rays_skipped;
   for (int i = 0; i < 3; ++i) {
     s.nodes[i] = h.nodes[i];
     s.tris[i] = h.tris[i];

@@ -17,6 +17,7 @@ struct RenderStats {
   unsigned long long rays_closest = 0;  // radiance rays traced
   unsigned long long rays_shadow = 0;   // visibility rays traced
   unsigned long long rays_light = 0;    // MIS rays traced
+  unsigned long long rays_skipped = 0;  // rays the reference traces whose contribution is exactly zero (not traced)
   unsigned long long launches = 0;      // kernels launched by the integrator
   // counting builds (set_traversal_counting): nodes visited / triangles tested per ray type
   unsigned long long nodes[3] = {0, 0, 0}, tris[3] = {0, 0, 0};

@@ -428,13 +428,18 @@ void Renderer::init_render_states() { m_impl->sample_count = 0; }
 void Renderer::render(const Camera& camera, const float3& bg_color, const RenderLayer& render_layer,
                       uint32_t n_samples, uint32_t max_depth)
 {
+  render(camera_params(camera), bg_color, render_layer, n_samples, max_depth);
+}
+
+CameraParams Renderer::camera_params(const Camera& camera) const
+{
   CameraParams cp;
   // a camera node of the scene overrides the application camera (renderer.h:671-685)
   cp.transform = rows_of(m_impl->scene.m_has_camera_transform ? m_impl->scene.m_camera_transform : camera.m_transform);
   cp.fov = camera.m_fov;
   cp.F = camera.m_F;
   cp.focus = camera.m_focus;
-  render(cp, bg_color, render_layer, n_samples, max_depth);
+  return cp;
 }
 
 void Renderer::render(const CameraParams& camera, const float3& bg_color, const RenderLayer& render_layer,
@@ -464,8 +469,10 @@ void Renderer::wait_for_completion()
 void Renderer::set_sample_offset(uint32_t first_sample) { m_impl->sample_count = first_sample; }
 uint32_t Renderer::get_sample_count() const { return m_impl->sample_count; }
 void Renderer::set_film_mode(FilmMode mode) { m_impl->film_mode = mode; }
+FilmMode Renderer::get_film_mode() const { return m_impl->film_mode; }
 void Renderer::scale_layers(const RenderLayer& render_layer, float scale)
 {
+  FR_CUDA_CHECK(cudaSetDevice(m_impl->device));
   m_impl->integrator->scale_layers(render_layer, m_impl->width * m_impl->height, scale);
 }
 void Renderer::set_max_wave_paths(size_t n_paths) { m_impl->integrator->set_max_wave_paths(n_paths); }
@@ -477,6 +484,7 @@ void Renderer::set_stage_timing(bool on) { m_impl->integrator->set_stage_timing(
 void Renderer::get_stage_times(double ms[kStageCount], unsigned long long launches[kStageCount])
 {
   static_assert(kStageCount == frd::STAGE_COUNT, "stage list out of sync");
+  FR_CUDA_CHECK(cudaSetDevice(m_impl->device));
   const frd::StageTimes t = m_impl->integrator->stage_times();
   for (int i = 0; i < kStageCount; ++i) {
     ms[i] = t.ms[i];
@@ -486,6 +494,7 @@ void Renderer::get_stage_times(double ms[kStageCount], unsigned long long launch
 
 RenderStatistics Renderer::get_statistics()
 {
+  FR_CUDA_CHECK(cudaSetDevice(m_impl->device));
   const frd::RenderStats s = m_impl->integrator->stats();
   RenderStatistics r;
   r.paths = s.paths;
@@ -493,13 +502,18 @@ RenderStatistics Renderer::get_statistics()
   r.rays_shadow = s.rays_shadow;
   r.rays_light = s.rays_light;
   r.kernel_launches = s.launches;
+  r.rays_skipped = s.rays_skipped;
   for (int i = 0; i < 3; ++i) {
     r.nodes_visited[i] = s.nodes[i];
     r.tris_tested[i] = s.tris[i];
   }
   return r;
 }
-void Renderer::reset_statistics() { m_impl->integrator->reset_stats(); }
+void Renderer::reset_statistics()
+{
+  FR_CUDA_CHECK(cudaSetDevice(m_impl->device));
+  m_impl->integrator->reset_stats();
+}
 AccelInfo Renderer::get_accel_info() const { return m_impl->accel_info; }
 cudaStream_t Renderer::get_stream() const { return m_impl->stream; }
 int Renderer::get_device() const { return m_impl->device; }

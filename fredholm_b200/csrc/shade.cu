@@ -196,6 +196,7 @@ __global__ void __launch_bounds__(kBlock, FRD_SHADE_BLOCKS) k_shade(WaveParams w
   uint32_t* q_out = wb.queue[(depth & 1u) ^ 1u];
   const SceneTex tex{sc.textures, sc.srgb_lut};
   uint32_t item;
+  uint32_t skipped = 0;  // visibility / MIS rays the reference would trace whose contribution is exactly zero
   while (fetch_batch(&ctl->cursor_class[cls], n, item)) {
     bool active = item < n;
     uint32_t slot = 0;
@@ -349,6 +350,7 @@ __global__ void __launch_bounds__(kBlock, FRD_SHADE_BLOCKS) k_shade(WaveParams w
           const float3 weight = regularize(throughput * mis * f * abs_cos(wi) / pdf);
           c = weight * le;
           want = nonzero3(c);  // a zero contribution needs no visibility test (NaN is kept)
+          skipped += want ? 0u : 1u;
         }
       }
       const uint32_t pos = queue_reserve(&ctl->n[Q_SHADOW0 + k], want);
@@ -379,6 +381,7 @@ __global__ void __launch_bounds__(kBlock, FRD_SHADE_BLOCKS) k_shade(WaveParams w
         if (s == 0) {
           w = throughput * f * cos_wi / pdf;
           want = nonzero3(w);
+          skipped += want ? 0u : 1u;
           if (sc.n_lights == 0) {
             // no emissive face anywhere: the MIS ray can only contribute by leaving the scene
             // (__miss__light, pt.cu:531-543), so its contribution is known here and the ray
@@ -417,6 +420,9 @@ __global__ void __launch_bounds__(kBlock, FRD_SHADE_BLOCKS) k_shade(WaveParams w
       }
     }
   }
+  // ray accounting only (the reference's trace-call count = traced + skipped): one atomic per warp and kernel
+  skipped = __reduce_add_sync(0xffffffffu, skipped);
+  if (lane_id() == 0 && skipped) atomicAdd(&ctl->rays_skipped, (unsigned long long)skipped);
 }
 
 // end of a bounce: rotate the radiance queue, clear the secondary queues and cursors

@@ -103,6 +103,7 @@ struct WaveControl {
   unsigned long long rays_closest, rays_shadow, rays_light;  // traced rays
   unsigned long long nodes[3], tris[3];  // counting builds only: per ray type (closest, shadow, MIS)
   unsigned long long paths;
+  unsigned long long rays_skipped;  // zero-contribution visibility / MIS rays that were not traced (shade.cu)
 };
 
 struct WaveBuffers {

@@ -41,6 +41,9 @@ struct RenderStatistics {
   unsigned long long rays_shadow = 0;
   unsigned long long rays_light = 0;
   unsigned long long kernel_launches = 0;
+  // visibility / MIS rays whose contribution is exactly zero: the reference traces them (pt.cu:766-925), this
+  // core does not.  total_rays() + rays_skipped = the reference's optixTrace call count for the same samples.
+  unsigned long long rays_skipped = 0;
   // only filled while set_traversal_counting(true): BVH nodes visited / triangles tested by the
   // radiance, shadow and MIS rays (index 0, 1, 2)
   unsigned long long nodes_visited[3] = {0, 0, 0};
@@ -105,6 +108,9 @@ class Renderer
   void set_sample_offset(uint32_t first_sample);  // next render starts at this sample index
   uint32_t get_sample_count() const;
   void set_film_mode(FilmMode mode);
+  FilmMode get_film_mode() const;
+  // the packed camera block render() uses for `camera` (a camera node of the scene overrides its transform)
+  CameraParams camera_params(const Camera& camera) const;
   void scale_layers(const RenderLayer& render_layer, float scale);
   void set_max_wave_paths(size_t n_paths);
   // One render(n_samples) call behaves like ONE reference launch of n_samples: payload.firsthit and the

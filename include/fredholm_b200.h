@@ -141,9 +141,40 @@ int fr_wait(fr_renderer* r);
  * and waits.  This is the call the end-to-end benchmark times. */
 int fr_render_frame_host(fr_renderer* r, const float* camera_transform12, float fov, float F, float focus,
                          const float* bg_color3, const fr_layers* layers_host, uint32_t n_samples, uint32_t max_depth);
+/* out4 = SM count, SM clock (kHz, the attribute's maximum), compute capability x 10, L2 bytes */
+int fr_get_device_attributes(int device, uint32_t* out4, uint64_t* total_mem);
 int fr_scale_layers(fr_renderer* r, const fr_layers* layers_dev, float scale);
-/* out5 = paths, radiance rays, shadow rays, light rays, kernel launches */
-int fr_get_statistics(fr_renderer* r, uint64_t* out5);
+
+/* ---- multi-GPU: sample-sharded render with ONE ncclReduce of the accumulation buffers, inside the C++ core
+ * (include/fredholm/multi_gpu.h; SURVEY.md 8(e): the reference is single-GPU, its batch application
+ * app/rtcamp8.cpp:159-246 is the caller shape).  NCCL is loaded at run time; without it these fail.
+ * (a) one rank per renderer -- threads of one process or one process per GPU: rank 0 makes the 128-byte id,
+ *     every rank calls fr_comm_init with the same bytes (collective), then fr_render_sharded (collective):
+ *     renders this rank's slice (fr_sample_slice: whole 16-sample CMJ patterns) of a total_spp frame into the
+ *     ZEROED layers as sums, reduces every bound layer onto `root` on the renderer's stream and divides by
+ *     total_spp there.  Asynchronous; fr_wait.  fr_reduce_layers is the exchange step alone. */
+int fr_comm_get_unique_id(uint8_t* out128);
+int fr_comm_init(fr_renderer* r, const uint8_t* id128, int rank, int world);
+int fr_comm_destroy(fr_renderer* r);
+int fr_sample_slice(uint32_t total_spp, int rank, int world, uint32_t* first, uint32_t* count);
+int fr_render_sharded(fr_renderer* r, const float* camera_transform12, float fov, float F, float focus,
+                      const float* bg_color3, const fr_layers* layers_dev, uint32_t total_spp, uint32_t max_depth,
+                      int root);
+int fr_reduce_layers(fr_renderer* r, const fr_layers* layers_dev, uint32_t total_spp, int root);
+/* (b) one process, n devices (NULL / 0: all): fredholm::MultiGpuRenderer, one renderer and one host thread per
+ *     device.  fr_multi_renderer returns the BORROWED handle of a rank for the scene / light / film calls above
+ *     (do not destroy it); fr_multi_render takes device pointers on the first device. */
+typedef struct fr_multi fr_multi;
+fr_multi* fr_multi_create(const int* devices, int n_devices);
+void fr_multi_destroy(fr_multi* m);
+int fr_multi_size(fr_multi* m);
+fr_renderer* fr_multi_renderer(fr_multi* m, int rank);
+int fr_multi_render(fr_multi* m, const float* camera_transform12, float fov, float F, float focus,
+                    const float* bg_color3, const fr_layers* layers_dev_rank0, uint32_t total_spp, uint32_t max_depth);
+int fr_multi_wait(fr_multi* m);
+/* out6 = paths, radiance rays, shadow rays, light rays, kernel launches, zero-contribution rays not traced
+ * (traced + not traced = the reference's trace-call count for the same samples) */
+int fr_get_statistics(fr_renderer* r, uint64_t* out6);
 int fr_reset_statistics(fr_renderer* r);
 /* measurement: counting instantiations of the traversal kernels (process-wide switch); out6 = CWBVH nodes
  * visited by radiance / shadow / MIS rays, then triangles tested by the same three, since the last reset */

@@ -42,6 +42,8 @@ def lib():
             raise RuntimeError("oracle library missing: run `make -C oracle` where /root/reference exists")
         L = C.CDLL(LIB_PATH)
         L.orc_render.restype = C.c_double
+        if hasattr(L, "orc_render_tiles"):
+            L.orc_render_tiles.restype = C.c_double
         L.orc_n_lights.restype = C.c_uint32
         L.orc_last_error.restype = C.c_char_p
         for n in ("orc_xxhash32_1", "orc_xxhash32_4", "orc_cmj_permute", "orc_sobol", "orc_owen",
@@ -185,13 +187,25 @@ class Oracle:
             C.c_uint32(max_depth), C.c_uint32(x0), C.c_uint32(y0), C.c_uint32(x1), C.c_uint32(y1),
             C.c_int(n_threads)))
 
-    def render_canonical(self, camera, bg_color, spp, max_depth, window=None, n_threads=1, layers=None):
+    def render_tiles(self, camera, bg_color, layers, n_samples, max_depth, tiles, n_threads=1):
+        """One launch over a list of windows [(x0, y0, x1, y1), ...]; returns seconds in the launch loop."""
+        t = np.ascontiguousarray(tiles, dtype=np.uint32).reshape(-1, 4)
+        return float(self.L.orc_render_tiles(
+            _f(_f32(camera.transform, 12)), C.c_float(camera.fov), C.c_float(camera.F), C.c_float(camera.focus),
+            _f(_f32(bg_color, 3)), _f(layers["beauty"]), _f(layers["position"]), _f(layers["depth"]),
+            _f(layers["normal"]), _f(layers["texcoord"]), _f(layers["albedo"]), C.c_uint32(n_samples),
+            C.c_uint32(max_depth), _u(t), C.c_uint32(len(t)), C.c_int(n_threads)))
+
+    def render_canonical(self, camera, bg_color, spp, max_depth, window=None, n_threads=1, layers=None, tiles=None):
         """`spp` launches of one sample each (what the reference GUI does,
         controller.cpp:221-224).  Returns (layers, seconds)."""
         layers = layers if layers is not None else self.new_layers()
         secs = 0.0
         for _ in range(spp):
-            secs += self.render(camera, bg_color, layers, 1, max_depth, window, n_threads)
+            if tiles is not None:
+                secs += self.render_tiles(camera, bg_color, layers, 1, max_depth, tiles, n_threads)
+            else:
+                secs += self.render(camera, bg_color, layers, 1, max_depth, window, n_threads)
         return layers, secs
 
     def ray_counts(self):

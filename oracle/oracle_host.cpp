@@ -865,6 +865,56 @@ double orc_render(const float* cam_transform12, float fov, float F, float focus,
   return std::chrono::duration<double>(t1 - t0).count();
 }
 
+// Same launch loop over a LIST of pixel windows (tiles4 = n_tiles x (x0, y0, x1, y1)): bench.py's reference arm
+// samples the frame in tiles spread over the whole image instead of one centre crop.  The work items handed
+// to the threads are tile rows.
+double orc_render_tiles(const float* cam_transform12, float fov, float F, float focus,
+                        const float* bg_color, float* beauty, float* position,
+                        float* depth, float* normal, float* texcoord, float* albedo,
+                        uint n_samples, uint max_depth, const uint* tiles4, uint n_tiles, int n_threads)
+{
+  if (!S->accel_valid) build_accel();
+  RenderLayer layers;
+  layers.beauty = reinterpret_cast<float4*>(beauty);
+  layers.position = reinterpret_cast<float4*>(position);
+  layers.depth = depth;
+  layers.normal = reinterpret_cast<float4*>(normal);
+  layers.texcoord = reinterpret_cast<float4*>(texcoord);
+  layers.albedo = reinterpret_cast<float4*>(albedo);
+  fill_params(cam_transform12, fov, F, focus, bg_color, layers, n_samples, max_depth);
+  struct Row {
+    uint y, x0, x1;
+  };
+  std::vector<Row> rows;
+  for (uint t = 0; t < n_tiles; ++t)
+    for (uint y = tiles4[4 * t + 1]; y < tiles4[4 * t + 3]; ++y) rows.push_back(Row{y, tiles4[4 * t], tiles4[4 * t + 2]});
+  n_threads = std::max(n_threads, 1);
+  std::atomic<size_t> next_row{0};
+  const auto worker = [&]() {
+    for (int k = 0; k < 3; ++k) g_rays[k] = 0;
+    for (;;) {
+      const size_t i = next_row.fetch_add(1);
+      if (i >= rows.size()) break;
+      for (uint x = rows[i].x0; x < rows[i].x1; ++x) {
+        g_ctx = TraceCtx{};
+        g_ctx.launch_index = make_uint3(x, rows[i].y, 0);
+        __raygen__rg();
+      }
+    }
+    for (int k = 0; k < 3; ++k) S->n_rays[k] += g_rays[k];
+  };
+  const auto t0 = std::chrono::steady_clock::now();
+  if (n_threads == 1) {
+    worker();
+  } else {
+    std::vector<std::thread> th;
+    for (int i = 0; i < n_threads; ++i) th.emplace_back(worker);
+    for (auto& t : th) t.join();
+  }
+  const auto t1 = std::chrono::steady_clock::now();
+  return std::chrono::duration<double>(t1 - t0).count();
+}
+
 void orc_get_ray_counts(unsigned long long* out3)
 {
   for (int k = 0; k < 3; ++k) out3[k] = S->n_rays[k];

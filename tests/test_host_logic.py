@@ -59,3 +59,23 @@ def test_procedural_scenes_are_deterministic():
     assert c.n_faces == 32
     # the benchmark scene has exactly 2^20 triangles (BASELINE.json config 2)
     assert 2 * 512 * 512 + 512 * (2 * 32 * 16) == 1048576
+
+
+def test_core_sample_slice_matches_the_python_rule():
+    """fr_sample_slice (C++ core, multi_gpu.cpp) and parallel.sample_slice (gloo tests) are the same partition:
+    contiguous, disjoint, covering, whole 16-sample CMJ patterns."""
+    from fredholm_b200 import api, parallel
+    for total in (0, 1, 15, 16, 17, 64, 100, 512, 4096, 4100):
+        for world in (1, 2, 3, 4, 8):
+            covered = 0
+            for rank in range(world):
+                first, cnt = api.sample_slice(total, rank, world)
+                assert (first, cnt) == parallel.sample_slice(total, rank, world)
+                assert first == covered
+                if rank < world - 1 or total % 16 == 0:
+                    assert cnt % 16 == 0 or first + cnt == total
+                covered += cnt
+            assert covered == total
+    import pytest
+    with pytest.raises(api.FredholmError):
+        api.sample_slice(64, 2, 2)

@@ -11,6 +11,7 @@ ap.add_argument("--width", type=int, default=1920)
 ap.add_argument("--height", type=int, default=1080)
 ap.add_argument("--frames", type=int, default=1)
 ap.add_argument("--spw", type=int, default=0)
+ap.add_argument("--stats-out", default="")
 a = ap.parse_args()
 s = scenes.standard_surface_scene()
 L = scenes.STANDARD_LIGHTING; C = scenes.STANDARD_CAMERA
@@ -21,5 +22,10 @@ r.set_resolution(a.width, a.height)
 if a.spw: r.set_samples_per_warp(a.spw)
 lay = DeviceLayers(a.width, a.height, names=("beauty",))
 for f in range(a.frames):
-    t0 = time.time(); r.render(cam, (0, 0, 0), lay, a.spp, a.depth); r.wait()
-    print("frame %d: %.3f s" % (f, time.time() - t0), r.statistics())
+    r.reset_statistics(); t0 = time.time(); r.render(cam, (0, 0, 0), lay, a.spp, a.depth); r.wait()
+    st = r.statistics()
+    print("frame %d: %.3f s" % (f, time.time() - t0), st)
+if a.stats_out:
+    import json
+    st["spp"] = a.spp; st["depth"] = a.depth
+    json.dump(st, open(a.stats_out, "w"))
