@@ -39,7 +39,7 @@ def to_ms(v, u):
 kernels = {}
 for r in rows[2:]:
     name = r[col["Kernel Name"]]
-    short = "k_trace_closest" if "k_trace_closest" in name else "k_trace_shadow" if "k_trace_shadow" in name else \\
+    short = "k_trace_closest" if "k_trace_closest" in name else "k_trace_shadow" if "k_trace_shadow" in name else \
             "k_trace_light" if "k_trace_light" in name else None
     if not short:
         continue
@@ -48,7 +48,7 @@ for r in rows[2:]:
     d = to_ms(num(r, "gpu__time_duration.sum"), unit("gpu__time_duration.sum"))
     k["launches"] += 1
     k["duration_ms"] += d
-    k["dram_bytes"] += to_bytes(num(r, "dram__bytes_read.sum"), unit("dram__bytes_read.sum")) + \\
+    k["dram_bytes"] += to_bytes(num(r, "dram__bytes_read.sum"), unit("dram__bytes_read.sum")) + \
         to_bytes(num(r, "dram__bytes_write.sum"), unit("dram__bytes_write.sum"))
     wi = num(r, "smsp__inst_executed.sum")
     k["warp_inst"] += wi
