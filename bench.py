@@ -305,9 +305,8 @@ def run_ours(args):
     r.set_max_wave_paths(wave_paths(args))
     dev = api.DeviceLayers(W, H, names=("beauty",))
     if world > 1:
-        ident = [api.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(ident, src=0)
-        r.comm_init(ident[0], rank, world)          # ncclCommInitRank inside the core
+        from fredholm_b200 import parallel
+        parallel.init_core_communicator(r, dist)    # rank 0's id through the process group, ncclCommInitRank inside the core
 
     def clear():
         dev.clear()

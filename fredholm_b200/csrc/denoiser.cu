@@ -210,6 +210,22 @@ Denoiser::Denoiser(uint32_t width, uint32_t height, const float4* d_beauty, cons
   m_impl->pong.alloc((size_t)width * height);
 }
 
+namespace
+{
+uint32_t on_device(int device, uint32_t width)
+{
+  FR_CUDA_CHECK(cudaSetDevice(device));
+  return width;
+}
+}  // namespace
+
+Denoiser::Denoiser(int context, uint32_t width, uint32_t height, const float4* d_beauty, const float4* d_normal,
+                   const float4* d_albedo, const float4* d_denoised, bool upscale)
+    : Denoiser(on_device(context, width), height, d_beauty, d_normal, d_albedo, const_cast<float4*>(d_denoised), upscale,
+               /*stream=*/0)
+{
+}
+
 Denoiser::~Denoiser() noexcept(false) {}
 
 void Denoiser::set_params(const DenoiserParams& params)

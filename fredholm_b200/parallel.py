@@ -56,3 +56,15 @@ def render_sharded(render_slice_sums, dist, total_spp, dst=0):
     first, n = sample_slice(total_spp, rank, world)
     sums = render_slice_sums(first, n)
     return reduce_film(dist, sums, total_spp, dst)
+
+
+def init_core_communicator(renderer, dist):
+    """Makes `renderer` one rank of the torch.distributed world INSIDE the C++ core (fr_comm_init ->
+    ncclCommInitRank): rank 0's 128-byte communicator id travels through the process group, after that the
+    sample-sharded render + reduce is one call, Renderer.render_sharded (fr_render_sharded).  Collective."""
+    from . import api
+    rank, world = dist.get_rank(), dist.get_world_size()
+    ident = [api.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ident, src=0)
+    renderer.comm_init(ident[0], rank, world)
+    return ident[0]

@@ -37,6 +37,10 @@ class Denoiser
  public:
   Denoiser(uint32_t width, uint32_t height, const float4* d_beauty, const float4* d_normal, const float4* d_albedo,
            float4* d_denoised, bool upscale = false, cudaStream_t stream = 0);
+  // the reference's argument order (denoiser.h:17-20: context first), so that applications written against it
+  // compile unchanged with include/optwl/optwl.h: `context` is the CUDA device index (optwl::Context::m_context)
+  Denoiser(int context, uint32_t width, uint32_t height, const float4* d_beauty, const float4* d_normal,
+           const float4* d_albedo, const float4* d_denoised, bool upscale = false);
   ~Denoiser() noexcept(false);
   Denoiser(const Denoiser&) = delete;
   Denoiser& operator=(const Denoiser&) = delete;

@@ -43,3 +43,29 @@ def test_cpp_application_renders(tmp_path):
     assert data.startswith(header)
     img = np.frombuffer(data[len(header):], np.uint8).reshape(96, 96, 3)
     assert img.mean() > 5 and img.std() > 1
+
+
+CWL_EXE = os.path.join(ROOT, "examples", "cwl_check")
+
+
+def build_cwl_check():
+    cmd = ["g++", "-std=c++17", "-O1", os.path.join(ROOT, "examples", "cwl_check.cpp"),
+           "-I" + os.path.join(ROOT, "include"), "-I/usr/local/cuda/include", "-L/usr/local/cuda/lib64", "-lcudart",
+           "-o", CWL_EXE]
+    subprocess.run(cmd, check=True)
+
+
+def test_cwl_headers_compile_and_fail_loudly_without_gpu():
+    """include/cwl/{buffer,util,texture}.h (reference cwl/include/cwl/*.h) are header-only over the CUDA runtime."""
+    build_cwl_check()
+    if api.lib().fr_device_count() > 0:
+        pytest.skip("CUDA device present")
+    p = subprocess.run([CWL_EXE], capture_output=True, text=True)
+    assert p.returncode == 1 and "CUDA call (cudaFree(0) ) failed" in p.stderr
+
+
+@pytest.mark.gpu
+def test_cwl_buffer_object_texture_on_the_gpu():
+    build_cwl_check()
+    p = subprocess.run([CWL_EXE], capture_output=True, text=True)
+    assert p.returncode == 0 and p.stdout.strip() == "ok", p.stderr
