@@ -111,6 +111,7 @@ SIGNATURES = {
     "fr_render_frame_host": (C.c_int, [_vp, _fp, C.c_float, C.c_float, C.c_float, _fp, C.POINTER(_Layers),
                                        C.c_uint32, C.c_uint32]),
     "fr_scale_layers": (C.c_int, [_vp, C.POINTER(_Layers), C.c_float]),
+    "fr_set_device": (C.c_int, [C.c_int]),
     "fr_get_device_attributes": (C.c_int, [C.c_int, _up, _u64p]),
     "fr_comm_get_unique_id": (C.c_int, [_u8p]),
     "fr_comm_init": (C.c_int, [_vp, _u8p, C.c_int, C.c_int]),
@@ -724,6 +725,11 @@ class Renderer:
         out = np.zeros_like(d)
         _check(lib().fr_sky_radiance(self._h, _f(d), len(d), _f(out)))
         return out
+
+
+def set_device(device):
+    """cudaSetDevice for this thread (fr_device_alloc / DeviceLayers allocate on the current device)."""
+    _check(lib().fr_set_device(int(device)))
 
 
 def device_attributes(device=0):

@@ -539,6 +539,11 @@ int fr_multi_wait(fr_multi* m)
   return guarded([&] { m->multi.wait_for_completion(); });
 }
 
+int fr_set_device(int device)
+{
+  return guarded([&] { FR_CUDA_CHECK(cudaSetDevice(device)); });
+}
+
 int fr_get_device_attributes(int device, uint32_t* out4, uint64_t* total_mem)
 {
   return guarded([&] {

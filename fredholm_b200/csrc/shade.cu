@@ -148,8 +148,9 @@ FR_D void load_surface_params(const fredholm::Material& m, const SceneTex& tex, 
   p.thin_walled = m.thin_walled;
 }
 
-// firefly clamp of the reference (pt.cu:373-376).  fmaxf(a, fminf(x, b)) maps NaN to b.
-FR_D float3 regularize(const float3& w) { return clamp3(w, 0.0f, 1.0f); }
+// firefly clamp of the reference (pt.cu:373-376): clamp(w, 0, 1) compiled by nvcc to .sat, i.e. NaN -> 0
+// (a NaN weight -- every lobe weight 0 on the back face of an opaque surface -- contributes nothing)
+FR_D float3 regularize(const float3& w) { return saturate3(w); }
 FR_D bool nonzero3(const float3& v) { return v.x != 0.0f || v.y != 0.0f || v.z != 0.0f; }
 
 constexpr float kShadowEps = 0.001f;  // SHADOW_RAY_EPS, pt.cu:11
@@ -387,14 +388,14 @@ __global__ void __launch_bounds__(kBlock, FRD_SHADE_BLOCKS) k_shade(WaveParams w
             // (__miss__light, pt.cu:531-543), so its contribution is known here and the ray
             // becomes a plain visibility ray (cosine pdf of the sky NEE strategy)
             const float mis = pdf / (pdf + cos_wi / kPi);
-            w = clamp3(w * mis, 0.0f, 1.0f) * sky_radiance(sc, dir);
+            w = saturate3(w * mis) * sky_radiance(sc, dir);
           }
         } else {
           throughput *= f * cos_wi / pdf;
           // raygen loop tail + head of the next iteration (pt.cu:455-471)
           want = !bad3(throughput) && depth + 1 < wp.max_depth;
           if (want) {
-            const float p = clampf(luminance(throughput), 0.0f, 1.0f);
+            const float p = saturate1(luminance(throughput));  // pt.cu:460, .sat on the device
             const float u = smp.next1d();
             want = !(u >= p);
             throughput = throughput / p;

@@ -220,7 +220,7 @@ struct LightPolicy {
     }
     if (contributes) {
       const float mis = pdf_bsdf / (pdf_bsdf + pdf_light);
-      const float3 ww = clamp3(f3(w.x * mis, w.y * mis, w.z * mis), 0.0f, 1.0f);
+      const float3 ww = saturate3(f3(w.x * mis, w.y * mis, w.z * mis));  // regularize_weight, pt.cu:373-376
       float4 L = wb.L[path];
       L.x += ww.x * le.x;
       L.y += ww.y * le.y;

@@ -56,6 +56,15 @@ FR_HD float3 normalize(const float3& v)
   return v * inv;
 }
 FR_HD float clampf(float f, float a, float b) { return fmaxf(a, fminf(f, b)); }
+// clamp(x, 0, 1) with the DEVICE semantics of the reference: nvcc lowers sutil's fmaxf(0, fminf(x, 1)) to the
+// .sat modifier, which maps NaN to 0 (oracle/Makefile, `make sat-evidence`).  __saturatef states that
+// explicitly instead of relying on the compiler's pattern match.
+#ifdef __CUDACC__
+FR_D float saturate1(float x) { return __saturatef(x); }
+#else
+inline float saturate1(float x) { return x != x ? 0.0f : fmaxf(0.0f, fminf(x, 1.0f)); }
+#endif
+FR_D float3 saturate3(const float3& v) { return make_float3(saturate1(v.x), saturate1(v.y), saturate1(v.z)); }
 FR_HD float3 clamp3(const float3& v, float a, float b)
 {
   return f3(clampf(v.x, a, b), clampf(v.y, a, b), clampf(v.z, a, b));

@@ -93,8 +93,9 @@ class MultiGpuRenderer
   void set_max_wave_paths(size_t n_paths);
 
   // total_spp samples per pixel, split over the devices; `layer` holds DEVICE pointers on devices[0]
-  // (the caller owns and clears them, as with Renderer::render); the other devices accumulate into
-  // buffers the object owns.  Asynchronous; wait_for_completion() synchronises every device.
+  // (the caller owns and clears them, as with Renderer::render; note that Renderer methods leave the calling
+  // thread on their own device, so allocate after cudaSetDevice(devices[0])); the other devices accumulate
+  // into buffers the object owns.  Asynchronous; wait_for_completion() synchronises every device.
   void render(const Camera& camera, const float3& bg_color, const RenderLayer& layer, uint32_t total_spp,
               uint32_t max_depth);
   void render(const CameraParams& camera, const float3& bg_color, const RenderLayer& layer, uint32_t total_spp,

@@ -141,6 +141,10 @@ int fr_wait(fr_renderer* r);
  * and waits.  This is the call the end-to-end benchmark times. */
 int fr_render_frame_host(fr_renderer* r, const float* camera_transform12, float fov, float F, float focus,
                          const float* bg_color3, const fr_layers* layers_host, uint32_t n_samples, uint32_t max_depth);
+/* cudaSetDevice for the calling thread: which device fr_device_alloc allocates on.  Every fr_* call on a
+ * renderer switches the calling thread to that renderer's device, so a process that drives several devices sets
+ * the device again before allocating caller-owned layers. */
+int fr_set_device(int device);
 /* out4 = SM count, SM clock (kHz, the attribute's maximum), compute capability x 10, L2 bytes */
 int fr_get_device_attributes(int device, uint32_t* out4, uint64_t* total_mem);
 int fr_scale_layers(fr_renderer* r, const fr_layers* layers_dev, float scale);

@@ -46,3 +46,24 @@ def make_cases(n_per_class=64, seed=7):
             rows.append(np.concatenate([sp, wo, [entering], wi, [u], v]))
             labels.append(name)
     return np.asarray(rows, dtype=np.float32), labels
+
+
+def make_cases_below_horizon(n_per_class=32, seed=13):
+    """wo BELOW the shading horizon (wo.y < 0).  The integrator flips the frame towards the viewer with the
+    GEOMETRIC normal; a normal / bump map can still tilt the shading normal away from the viewer, so these
+    directions do reach BSDF::eval (pt.cu:709-742, 762-763).  Used for the eval columns only: sampling from
+    below the horizon is ill-conditioned in the reference itself (0/0 pdfs)."""
+    rng = np.random.default_rng(seed)
+    rows, labels = [], []
+    for name, kw in MATERIAL_CLASSES.items():
+        sp = shading_params(**kw)
+        for i in range(n_per_class):
+            wo = rng.normal(size=3)
+            wo[1] = -(abs(wo[1]) + 0.02)
+            wo /= np.linalg.norm(wo)
+            wi = rng.normal(size=3)
+            wi /= np.linalg.norm(wi)
+            entering = 1.0 if (i % 4) != 3 else 0.0
+            rows.append(np.concatenate([sp, wo, [entering], wi, [rng.uniform()], rng.uniform(size=2)]))
+            labels.append(name)
+    return np.asarray(rows, dtype=np.float32), labels

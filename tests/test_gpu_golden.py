@@ -40,15 +40,38 @@ def test_bsdf_golden():
     g = golden("bsdf.npz")
     got = api.bsdf_eval_sample(g["cases"]).astype(np.float64)
     want = g["out"].astype(np.float64)
-    nan_mismatch = np.isnan(got) != np.isnan(want)
-    assert nan_mismatch.mean() < 1e-3
+    # HARD bounds on every case (no percentile): measured maxima on the B200 with shade.cu's -use_fast_math are
+    # eval 5.6e-6, sampled direction 8.2e-5, sampled f / pdf 4.3e-4 (9.2e-3 for clear_glass, roughness 0.01),
+    # f / pdf ratio 4e-5 (tests/tools/dbg_bsdf_tail.py).  NaN must appear in exactly the same places.
+    assert not (np.isnan(got) != np.isnan(want)).any()
     err = np.abs(got - want) / (np.abs(want) + 1e-3)
     err[np.isnan(err)] = 0
     labels = g["labels"]
+    assert err[:, :4].max() < 2e-5, err[:, :4].max()            # eval f, pdf
+    assert err[:, 4:7].max() < 3e-4, err[:, 4:7].max()          # sampled direction
     for cls in dict.fromkeys(labels.tolist()):
-        e = err[labels == cls]
-        assert np.quantile(e, 0.99) < 2e-3, (cls, np.quantile(e, 0.99))
+        e = err[labels == cls][:, 7:]
+        # alpha = roughness^2 = 1e-4 for clear_glass: D ~ 1 / alpha^2 turns one ulp of cos(theta_h) into 1e-3 of f
+        bound = 2e-2 if cls == "clear_glass" else 1e-3
+        assert e.max() < bound, (cls, e.max())
+    # what the integrator multiplies the throughput with is f / pdf: the peaky factors cancel
+    ok = np.isfinite(want[:, 10]) & (want[:, 10] > 0) & np.isfinite(got[:, 10])
+    ratio_g = got[ok, 7:10] / got[ok, 10:11]
+    ratio_w = want[ok, 7:10] / want[ok, 10:11]
+    assert (np.abs(ratio_g - ratio_w) / (np.abs(ratio_w) + 1e-3)).max() < 3e-4
     assert np.median(err) < 1e-5
+
+
+def test_bsdf_golden_below_the_shading_horizon():
+    """wo.y < 0 (reachable through normal / bump maps only): eval f and pdf of every material class against the
+    reference BSDF, hard bound on every case."""
+    g = golden("bsdf_below_horizon.npz")
+    got = api.bsdf_eval_sample(g["cases"]).astype(np.float64)[:, :4]
+    want = g["out"].astype(np.float64)
+    assert not (np.isnan(got) != np.isnan(want)).any()
+    err = np.abs(got - want) / (np.abs(want) + 1e-3)
+    err[np.isnan(err)] = 0
+    assert err.max() < 5e-5, err.max()
 
 
 def test_sky_golden(renderer):

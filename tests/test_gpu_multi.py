@@ -77,6 +77,7 @@ def test_multi_renderer_matches_single_gpu(single):
     n = len(m)
     assert n == api.lib().fr_device_count()
     m.for_each(_setup)
+    api.set_device(0)     # the result layers live on the first device (every renderer call switches the thread's device)
     lay = DeviceLayers(W, H, names=("beauty", "albedo", "depth"))
     lay.clear()
     m.render(_camera(), (0, 0, 0), lay, SPP, DEPTH)

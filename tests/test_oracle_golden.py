@@ -180,3 +180,12 @@ def test_sample_slices_compose(oracle_mod):
     sum1 = parts[1]
     combined = (mean0 * 8.0 + sum1) / 16.0
     assert np.allclose(combined[..., :3], full["beauty"][..., :3], rtol=1e-4, atol=1e-5)
+
+
+def test_bsdf_golden_below_the_shading_horizon(oracle_mod):
+    """wo.y < 0 (reachable through normal / bump maps): the committed eval table is what the reference BSDF gives."""
+    g = golden("bsdf_below_horizon.npz")
+    got = oracle_mod.bsdf_eval_sample(g["cases"])[:, :4]
+    assert np.array_equal(np.isnan(got), np.isnan(g["out"]))
+    assert np.allclose(got, g["out"], rtol=1e-6, atol=0, equal_nan=True)
+    assert (g["cases"][:, 31] < 0).all() and np.isfinite(g["out"]).mean() > 0.9

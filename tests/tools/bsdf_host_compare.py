@@ -54,3 +54,14 @@ if len(sys.argv) > 1:
         print("wo", c[30:33], "entering", c[33], "u", c[37], "v", c[38:40])
         print("   ours wi", a[i, 4:7], "f", a[i, 7:10], "pdf", a[i, 10])
         print("   ref  wi", b[i, 4:7], "f", b[i, 7:10], "pdf", b[i, 10])
+
+if len(sys.argv) > 2 and sys.argv[2] == "nan":
+    cls = sys.argv[1]
+    cases, labels = make(400, 11, -1)
+    s = labels == cls
+    a = host(cases[s]); b = ob.bsdf_eval_sample(cases[s])
+    bad = np.where((np.isnan(a) != np.isnan(b)).any(axis=1))[0]
+    for i in bad:
+        c = cases[s][i]
+        print("wo", c[30:33], "entering", c[33], "u", c[37], "v", c[38:40])
+        print("   ours", a[i, 4:]); print("   ref ", b[i, 4:])

@@ -18,7 +18,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-from bsdf_cases import make_cases  # noqa: E402
+from bsdf_cases import make_cases, make_cases_below_horizon  # noqa: E402
 from fredholm_b200 import Camera, scenes  # noqa: E402
 from oracle import binding as ob  # noqa: E402
 
@@ -50,10 +50,21 @@ def small_standard_oracle(o):
     return s
 
 
+def bsdf_below_horizon():
+    """wo below the shading horizon (normal maps): eval f / pdf of the reference BSDF (round 2)."""
+    cases, labels = make_cases_below_horizon(32)
+    np.savez_compressed(os.path.join(OUT, "bsdf_below_horizon.npz"), cases=cases, labels=np.array(labels),
+                        out=ob.bsdf_eval_sample(cases)[:, :4])
+
+
 def main():
     if not ob.available():
         ob.build()
     os.makedirs(OUT, exist_ok=True)
+    if sys.argv[1:] == ["bsdf_below_horizon"]:   # add this fixture without touching the others
+        bsdf_below_horizon()
+        return
+    bsdf_below_horizon()
 
     # ---- integer sampler: CMJ + Owen-Sobol + xxhash (bit exact) ----
     seqs = np.stack([ob.sampler_sequence(w, h, 1, idx, spp, SAMPLER_KINDS) for (w, h, idx, spp) in SAMPLER_POINTS])
