@@ -489,8 +489,9 @@ def run_ours(args):
         "config": {"workload": workload_name(args, scene), "samples_per_gpu": spp, "parallelism": "sample-sharded x%d" % world,
                    "collective": None if world == 1 else "one ncclReduce of the beauty sums per frame, issued by the C++ core (fr_render_sharded)",
                    "wave_paths": wave_paths(args),
+                   "wave_state_gb": round(r.wave_state_bytes() / 1e9, 2),
                    "l2": "per-step working set (path state + queues, %.1f GB) exceeds the 126 MB L2; no explicit flush"
-                         % (r_state_gb(W, H, spp, args)),
+                         % (r.wave_state_bytes() / 1e9),
                    "bvh": {"nodes": accel["n_nodes"], "depth": accel["depth"], "build_ms": round(accel["build_ms"], 2),
                            "bytes": accel["bytes"]}},
         "mrays_per_s": rays_all / secs / 1e6,
@@ -537,15 +538,6 @@ def wave_paths(args):
     """All samples of the frame in ONE wave unless overridden: fewer, larger launches (the
     persistent kernels have a fixed tail per launch) at the price of HBM for the wave state."""
     return args.wave_paths or slots_per_sample(args.width, args.height) * args.spp
-
-
-PATH_STATE_BYTES = 8 * 16 + (2 + 9) * 4 + 4 * 48   # path SoA + queues (integrator.cpp: ensure_capacity)
-
-
-def r_state_gb(W, H, spp, args):
-    slots = slots_per_sample(W, H)
-    per_wave = max(1, min(spp, wave_paths(args) // slots))
-    return per_wave * slots * PATH_STATE_BYTES / 1e9
 
 
 def main():

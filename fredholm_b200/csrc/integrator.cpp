@@ -135,7 +135,29 @@ void Integrator::ensure_capacity(size_t n_slots)
     throw;
   }
   m_capacity = n_slots;
-  m_state_bytes = n_slots * kWaveBytesPerSlot;
+}
+
+// Buffers only some renders need -- the first-hit AOV words (48 B / path), the sun and area-light NEE queues
+// (48 B / path each), the coherence-sort scratch (8 B / path) -- are allocated when a render first needs them, at
+// the capacity of the core set: a beauty-only render of a scene without emitters keeps 268 B / path instead of 372.
+void Integrator::ensure_optional(const WaveNeeds& need)
+{
+  bool synced = false;
+  auto grow = [&](auto& buf, bool wanted) {
+    if (!wanted || buf.size() >= m_capacity) return;
+    if (!synced) FR_CUDA_CHECK(cudaStreamSynchronize(m_stream));
+    synced = true;
+    buf.alloc(m_capacity);
+  };
+  grow(m_aov0, need.aov);
+  grow(m_aov1, need.aov);
+  grow(m_aov2, need.aov);
+  grow(m_shadow[0], need.sun_queue);
+  grow(m_shadow[2], need.area_queue);
+  grow(m_sort_keys, need.sort);
+  grow(m_sort_out, need.sort);
+  m_state_bytes = m_capacity * kWaveBytesCore + m_aov0.bytes() + m_aov1.bytes() + m_aov2.bytes() + m_shadow[0].bytes() +
+                  m_shadow[2].bytes() + m_sort_keys.bytes() + m_sort_out.bytes();
 }
 
 void Integrator::release_wave_buffers()
@@ -165,16 +187,19 @@ void Integrator::grow_wave_buffers(size_t n_slots)
   m_hit.alloc(n_slots);
   m_thr.alloc(n_slots);
   m_L.alloc(n_slots);
-  m_aov0.alloc(n_slots);
-  m_aov1.alloc(n_slots);
-  m_aov2.alloc(n_slots);
   m_queue[0].alloc(n_slots);
   m_queue[1].alloc(n_slots);
-  for (auto& s : m_shadow) s.alloc(n_slots);
+  m_shadow[1].alloc(n_slots);
   for (auto& q : m_class_queue) q.alloc(n_slots);
   m_light.alloc(n_slots);
-  m_sort_keys.alloc(n_slots);
-  m_sort_out.alloc(n_slots);
+  // the optional sets follow on demand (ensure_optional); what exists is dropped so that it regrows to the new size
+  m_aov0.release();
+  m_aov1.release();
+  m_aov2.release();
+  m_shadow[0].release();
+  m_shadow[2].release();
+  m_sort_keys.release();
+  m_sort_out.release();
 }
 
 void Integrator::render(const SceneView& scene, const fredholm::CameraParams& camera, uint32_t width,
@@ -186,6 +211,11 @@ void Integrator::render(const SceneView& scene, const fredholm::CameraParams& ca
   uint32_t spw_log2 = m_spw_log2;
   while (spw_log2 > 0 && (1u << spw_log2) > n_samples) spw_log2--;
   const FilmGeom film = make_film_geom(width, height, spw_log2);
+  WaveNeeds need;
+  need.aov = (layers.position || layers.normal || layers.depth || layers.texcoord || layers.albedo) && !m_single_launch;
+  need.sun_queue = scene.has_dir_light != 0;
+  need.area_queue = scene.n_lights > 0;
+  need.sort = m_sort_mask != 0;
   // a wave = whole sample groups (spw samples of every pixel), at least one
   size_t groups_per_wave = std::max<size_t>(
       1, std::min<size_t>(film_groups(film, n_samples), m_max_wave_paths / film.slots_per_group));
@@ -193,11 +223,12 @@ void Integrator::render(const SceneView& scene, const fredholm::CameraParams& ca
     // growing: never ask for more than the device can give (90 % of what is free plus what the wave holds now)
     size_t free_b = 0, total_b = 0;
     FR_CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
-    const size_t fit = (size_t)(0.9 * (double)(free_b + m_state_bytes)) / (kWaveBytesPerSlot * film.slots_per_group);
+    const size_t fit = (size_t)(0.9 * (double)(free_b + m_state_bytes)) / (wave_bytes_per_slot(need) * film.slots_per_group);
     groups_per_wave = std::max<size_t>(1, std::min(groups_per_wave, fit));
   }
   const uint32_t per_wave = (uint32_t)(groups_per_wave << spw_log2);
   ensure_capacity(groups_per_wave * film.slots_per_group);
+  ensure_optional(need);
 
   WaveBuffers wb;
   wb.ray_o = m_ray_o.get();

@@ -84,10 +84,21 @@ class Integrator
   ~Integrator();
 
  private:
-  // wave state per path slot: 8 float4 words, 2 + CLS_COUNT queue entries, 3 shadow + 1 MIS ray records, sort scratch
-  static constexpr size_t kWaveBytesPerSlot = 8 * sizeof(float4) + (2 + CLS_COUNT) * sizeof(uint32_t) +
-                                              3 * sizeof(ShadowRay) + sizeof(LightRay) + 2 * sizeof(uint32_t);
+  // wave state per path slot.  Core set: 5 float4 words (ray origin, direction, hit, throughput, radiance),
+  // 2 + CLS_COUNT queue entries, the sky-NEE and MIS ray records = 220 B; optional sets: first-hit AOV words
+  // (3 float4), sun / area-light NEE records (48 B each), coherence-sort scratch (8 B)
+  static constexpr size_t kWaveBytesCore = 5 * sizeof(float4) + (2 + CLS_COUNT) * sizeof(uint32_t) + sizeof(ShadowRay) +
+                                           sizeof(LightRay);
+  struct WaveNeeds {
+    bool aov = false, sun_queue = false, area_queue = false, sort = false;
+  };
+  static constexpr size_t wave_bytes_per_slot(const WaveNeeds& n)
+  {
+    return kWaveBytesCore + (n.aov ? 3 * sizeof(float4) : 0) + (n.sun_queue ? sizeof(ShadowRay) : 0) +
+           (n.area_queue ? sizeof(ShadowRay) : 0) + (n.sort ? 2 * sizeof(uint32_t) : 0);
+  }
   void ensure_capacity(size_t n_slots);
+  void ensure_optional(const WaveNeeds& need);
   void grow_wave_buffers(size_t n_slots);
   void release_wave_buffers();
 

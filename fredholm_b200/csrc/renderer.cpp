@@ -476,6 +476,7 @@ void Renderer::scale_layers(const RenderLayer& render_layer, float scale)
   m_impl->integrator->scale_layers(render_layer, m_impl->width * m_impl->height, scale);
 }
 void Renderer::set_max_wave_paths(size_t n_paths) { m_impl->integrator->set_max_wave_paths(n_paths); }
+size_t Renderer::get_wave_state_bytes() const { return m_impl->integrator->state_bytes(); }
 void Renderer::set_single_launch(bool on) { m_impl->integrator->set_single_launch(on); }
 void Renderer::set_samples_per_warp(uint32_t spw) { m_impl->integrator->set_samples_per_warp(spw); }
 void Renderer::set_traversal_counting(bool on) { frd::set_traversal_counting(on); }

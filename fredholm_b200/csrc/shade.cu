@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(kGenBlock) k_generate(WaveParams wp, WaveBuffe
     const bool inside = slot_to_pixel(wp.film, slot, x, y, sample) && sample < wp.n_samples;
     wb.L[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (wp.single_launch) wb.hit[slot] = make_float4(0.f, 0.f, 0.f, __uint_as_float(kNoHit));  // read by k_first_hit
-    if (wp.want_aov) {  // the first-hit words are only kept when a layer will read them
+    if (wp.want_aov && !wp.single_launch) {  // the first-hit words are only kept when a layer will read them
       wb.aov0[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
       wb.aov1[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
       wb.aov2[slot] = make_float4(0.f, 0.f, 0.f, 0.f);

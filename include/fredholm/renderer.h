@@ -113,6 +113,7 @@ class Renderer
   CameraParams camera_params(const Camera& camera) const;
   void scale_layers(const RenderLayer& render_layer, float scale);
   void set_max_wave_paths(size_t n_paths);
+  size_t get_wave_state_bytes() const;  // device memory the integrator holds for path state and ray queues
   // One render(n_samples) call behaves like ONE reference launch of n_samples: payload.firsthit and the
   // first-hit AOVs outlive the sample loop (pt.cu:432-433, 744-759) -- what app/rtcamp8.cpp produces.  Off by
   // default: render(n_samples) equals n_samples launches of one sample, what the reference GUI produces.
