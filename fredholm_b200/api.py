@@ -87,6 +87,8 @@ SIGNATURES = {
     "fr_set_scene": (C.c_int, [_vp, _vp]),
     "fr_build_accel": (C.c_int, [_vp]),
     "fr_get_accel_info": (C.c_int, [_vp, _up, _fp, _u64p]),
+    "fr_set_accel_mode": (C.c_int, [_vp, C.c_int]),
+    "fr_get_accel_info2": (C.c_int, [_vp, _up, C.POINTER(C.c_float)]),
     "fr_get_accel_data": (C.c_int, [_vp, _vp, _vp]),
     "fr_set_time": (C.c_int, [_vp, C.c_float]),
     "fr_set_transforms": (C.c_int, [_vp, _fp, C.c_uint32]),
@@ -506,8 +508,18 @@ class Renderer:
         ms = C.c_float()
         nbytes = C.c_uint64()
         _check(lib().fr_get_accel_info(self._h, _u(out), C.byref(ms), C.byref(nbytes)))
+        out5 = np.zeros(5, np.uint32)
+        tlas_ms = C.c_float()
+        _check(lib().fr_get_accel_info2(self._h, _u(out5), C.byref(tlas_ms)))
         return dict(n_faces=int(out[0]), n_nodes=int(out[1]), depth=int(out[2]), build_ms=ms.value,
-                    bytes=int(nbytes.value))
+                    bytes=int(nbytes.value), two_level=bool(out5[0]), n_instances=int(out5[1]), n_meshes=int(out5[2]),
+                    n_stored_faces=int(out5[3]), tlas_update_ms=tlas_ms.value)
+
+    ACCEL_MODES = {"auto": 0, "flat": 1, "two_level": 2}
+
+    def set_accel_mode(self, mode):
+        """"auto" | "flat" | "two_level" (include/fredholm/renderer.h AccelMode); applies at the next build_accel."""
+        _check(lib().fr_set_accel_mode(self._h, self.ACCEL_MODES[mode]))
 
     NODE_DTYPE = np.dtype([("p", "<f4", 3), ("e", "u1", 3), ("imask", "u1"), ("child_base", "<u4"),
                            ("tri_base", "<u4"), ("meta", "u1", 8), ("qlo", "u1", (3, 8)), ("qhi", "u1", (3, 8))])
@@ -517,7 +529,8 @@ class Renderer:
         (xyz + face id / flags bits in w)."""
         info = self.accel_info()
         nodes = np.zeros(info["n_nodes"], self.NODE_DTYPE)
-        tris = np.zeros((info["n_faces"], 3, 4), np.float32)
+        n_tris = info["n_instances"] + info["n_stored_faces"] if info["two_level"] else info["n_faces"]
+        tris = np.zeros((n_tris, 3, 4), np.float32)
         _check(lib().fr_get_accel_data(self._h, nodes.ctypes.data_as(_vp), tris.ctypes.data_as(_vp)))
         return nodes, tris
 

@@ -43,9 +43,20 @@ struct alignas(16) LeafTri {
   float4 v0, v1, v2;
 };
 
+// Two-level mode (instanced scenes, set_time without a rebuild): the node / triangle arrays hold an instance tree
+// (TLAS) at index 0 followed by one object-space tree (BLAS) per DISTINCT mesh.  A TLAS "triangle" is a
+// placeholder whose three vertices span the instance's world box; its v0.w is the instance index.  All child /
+// triangle indices are absolute.  instances == nullptr: one flat world-space tree (the default).
+struct InstanceRecord {
+  uint32_t blas_root;    // node index of the mesh's root
+  uint32_t face_offset;  // global face index of the instance's first face (BLAS triangles carry mesh-local ids)
+};
+
 struct BvhView {
   const float4* nodes;  // Node8 as float4[5]
   const float4* tris;   // LeafTri as float4[3]
+  const InstanceRecord* instances;  // two-level mode only
+  const float4* w2o;                // world-to-object rows, 3 float4 per instance (two-level mode only)
 };
 
 struct HitRecord {
@@ -200,6 +211,7 @@ struct NoAnyHit {
 //
 // Closest hit (ANY = false) or first accepted hit (ANY = true).
 // Tie rule on exactly equal t: lower global face index wins (as in the oracle).
+template <bool TWO>
 struct Traverser {
   float3 o;
   RayShear sh;
@@ -211,14 +223,29 @@ struct Traverser {
   uint2 tgroup;   // pending triangles: x = triangle base, y = 24-bit mask
   uint2 tgroup2;  // second parking slot
   TravStack st;
+  // two-level mode: the instance being traversed (kNoHit: in the TLAS) and the stack height its tree started at
+  uint32_t inst;
+  int sp_base;
 
   FR_D void begin(const float3& org, const float3& d, float t_min, float t_max)
   {
-    o = org;
     tmin = t_min;
     best.t = t_max;
     best.u = best.v = 0.0f;
     best.face = kNoHit;
+    set_ray(org, d);
+    st.sp = 0;
+    ngroup = make_uint2(0u, 0x80000000u);
+    tgroup = make_uint2(0u, 0u);
+    tgroup2 = make_uint2(0u, 0u);
+    inst = kNoHit;
+    sp_base = 0;
+  }
+
+  // direction-dependent constants of the ray (shear, reciprocal direction, octant)
+  FR_D void set_ray(const float3& org, const float3& d)
+  {
+    o = org;
     sh = make_shear(d);
     // box tests are conservative: guard against 0 * inf and widen by a few ulps
     const float tiny = 1e-20f;
@@ -227,16 +254,51 @@ struct Traverser {
                          fabsf(d.z) > tiny ? d.z : copysignf(tiny, d.z));
     idir = f3(1.0f / ds.x, 1.0f / ds.y, 1.0f / ds.z);
     octinv = (d.x >= 0.0f ? 1u : 0u) | (d.y >= 0.0f ? 2u : 0u) | (d.z >= 0.0f ? 4u : 0u);
-    st.sp = 0;
-    ngroup = make_uint2(0u, 0x80000000u);
+  }
+
+  // ---- two-level mode -------------------------------------------------------------------------
+  // The instance's tree is walked with the ray taken to object space, o' = W2O o, d' = W2O d (not
+  // normalised, so t is the same parameter in both spaces and `best` carries over).  What is left of the
+  // TLAS walk -- node group, parked placeholders -- goes on the stack; sp_base marks where the instance's own
+  // stack starts.  The world ray is not kept: the policy reloads it from the queue record on the way back.
+  FR_D bool in_instance() const { return TWO && inst != kNoHit; }
+  FR_D bool instance_done() const { return TWO && inst != kNoHit && ngroup.y == 0u && tgroup.y == 0u; }
+  FR_D int stack_floor() const { return TWO ? sp_base : 0; }
+
+  FR_D void enter_instance(const BvhView& bvh, uint32_t instance, const float3& wo, const float3& wd)
+  {
+    st.push(ngroup);
+    st.push(tgroup);
+    st.push(tgroup2);
+    const float4 r0 = __ldg(bvh.w2o + 3ull * instance), r1 = __ldg(bvh.w2o + 3ull * instance + 1),
+                 r2 = __ldg(bvh.w2o + 3ull * instance + 2);
+    const float3 oo = f3(r0.x * wo.x + r0.y * wo.y + r0.z * wo.z + r0.w, r1.x * wo.x + r1.y * wo.y + r1.z * wo.z + r1.w,
+                         r2.x * wo.x + r2.y * wo.y + r2.z * wo.z + r2.w);
+    const float3 od = f3(r0.x * wd.x + r0.y * wd.y + r0.z * wd.z, r1.x * wd.x + r1.y * wd.y + r1.z * wd.z,
+                         r2.x * wd.x + r2.y * wd.y + r2.z * wd.z);
+    set_ray(oo, od);
+    inst = instance;
+    sp_base = st.sp;
+    ngroup = make_uint2(bvh.instances[instance].blas_root, 0x80000000u);
     tgroup = make_uint2(0u, 0u);
     tgroup2 = make_uint2(0u, 0u);
+  }
+
+  // back to the TLAS walk with the world ray (wo, wd)
+  FR_D void leave_instance(const float3& wo, const float3& wd)
+  {
+    tgroup2 = st.pop();
+    tgroup = st.pop();
+    ngroup = st.pop();
+    inst = kNoHit;
+    sp_base = 0;
+    set_ray(wo, wd);
   }
 
   FR_D bool has_triangles() const { return tgroup.y != 0u; }
   // node work available and a free slot to park the triangles it may produce
   FR_D bool can_descend() const { return ngroup.y != 0u && tgroup2.y == 0u; }
-  FR_D bool finished() const { return ngroup.y == 0u && tgroup.y == 0u; }
+  FR_D bool finished() const { return ngroup.y == 0u && tgroup.y == 0u && !in_instance(); }
 
   template <bool COUNT>
   FR_D void node_phase(const BvhView& bvh, TraceCounters* cnt)
@@ -301,7 +363,7 @@ struct Traverser {
       ngroup.x = __float_as_uint(n1.x);
       ngroup.y = (hitmask & 0xff000000u) | (ew >> 24);
     } else if (ngroup.y <= 0x00ffffffu) {
-      ngroup = st.sp > 0 ? st.pop() : make_uint2(0u, 0u);
+      ngroup = st.sp > stack_floor() ? st.pop() : make_uint2(0u, 0u);
     }
     // park the leaf triangles this node produced
     const uint32_t tmask = hitmask & 0x00ffffffu;
@@ -315,12 +377,36 @@ struct Traverser {
   }
 
   // tests ONE pending triangle; returns true if an ANY ray found its hit
-  template <bool ANY, bool COUNT, typename AnyHit>
-  FR_D bool triangle_phase(const BvhView& bvh, const AnyHit& anyhit, TraceCounters* cnt)
+  // Policy: world_ray(o, d) reloads the lane's ray (two-level mode only)
+  template <bool ANY, bool COUNT, typename AnyHit, typename Policy>
+  FR_D bool triangle_phase(const BvhView& bvh, const AnyHit& anyhit, TraceCounters* cnt, Policy& pol)
   {
     const uint32_t bit = __ffs(tgroup.y) - 1u;
     tgroup.y &= tgroup.y - 1u;
     const float4* tp = bvh.tris + 3ull * (tgroup.x + bit);
+    if (TWO && inst == kNoHit) {
+      // a TLAS leaf entry: the placeholder of an instance (its box was tested with the node); walk its tree
+      const float4 lo = __ldg(tp), hi = __ldg(tp + 1);  // the placeholder's v0 / v1 are the corners of the world box
+      const uint32_t instance = __float_as_uint(lo.w);
+      if (tgroup.y == 0u) {
+        tgroup = tgroup2;
+        tgroup2 = make_uint2(0u, 0u);
+      }
+      // Entering costs a ray transform and a walk from the mesh's root, and the placeholder may have been parked
+      // before a closer hit was found: test its exact box against the CURRENT best.t first (conservative slabs).
+      {
+        const float ax = (lo.x - o.x) * idir.x, bx = (hi.x - o.x) * idir.x;
+        const float ay = (lo.y - o.y) * idir.y, by = (hi.y - o.y) * idir.y;
+        const float az = (lo.z - o.z) * idir.z, bz = (hi.z - o.z) * idir.z;
+        const float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), tmin)) * 0.9999995f;
+        const float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), best.t)) * 1.0000005f;
+        if (!(tn <= tf)) return false;
+      }
+      float3 wo, wd;
+      pol.world_ray(wo, wd);
+      enter_instance(bvh, instance, wo, wd);
+      return false;
+    }
     const float4 v0 = __ldg(tp + 0), v1 = __ldg(tp + 1), v2 = __ldg(tp + 2);
     if (tgroup.y == 0u) {
       tgroup = tgroup2;
@@ -329,7 +415,7 @@ struct Traverser {
     if (COUNT) cnt->tris++;
     float t, u, v;
     if (!watertight_hit(sh, o, v0, v1, v2, tmin, best.t, best.face != kNoHit, t, u, v)) return false;
-    const uint32_t face = __float_as_uint(v0.w);
+    const uint32_t face = __float_as_uint(v0.w) + (TWO ? bvh.instances[inst].face_offset : 0u);
     if (t == best.t && best.face != kNoHit && face > best.face) return false;
     if ((__float_as_uint(v1.w) & 1u) && !anyhit(face, u, v)) return false;
     best.t = t;
@@ -354,17 +440,20 @@ struct Traverser {
 //   void load(uint32_t item, float3& o, float3& d, float& tmin, float& tmax)  (lane-local payload)
 //   void retire(bool has_result, const HitRecord& h, const TraceCounters&)    all 32 lanes together
 //   anyhit()                                                                  alpha-test functor
-template <bool ANY, bool COUNT, typename Policy>
+//   void world_ray(float3& o, float3& d)                                       two-level mode: reload the ray
+template <bool ANY, bool COUNT, bool TWO, typename Policy>
 FR_D void trace_queue(const BvhView& bvh, Policy& pol, uint32_t* cursor, uint32_t n, uint2* smem_column,
                       int stride, int refill_lanes, int tri_lanes)
 {
   uint2 overflow[kLocalStack];
-  Traverser tr;
+  Traverser<TWO> tr;
   tr.st.smem = smem_column;
   tr.st.stride = stride;
   tr.st.local = overflow;
   tr.st.sp = 0;
   tr.ngroup = tr.tgroup = tr.tgroup2 = make_uint2(0u, 0u);
+  tr.inst = kNoHit;
+  tr.sp_base = 0;
   TraceCounters cnt{0u, 0u};
   const uint32_t lane = threadIdx.x & 31u;
   bool have = false;      // lane is traversing a ray
@@ -418,10 +507,16 @@ FR_D void trace_queue(const BvhView& bvh, Policy& pol, uint32_t* cursor, uint32_
     const uint32_t node_votes = __ballot_sync(0xffffffffu, have && tr.can_descend());
     bool done = false;
     if (tri_votes != 0u && (__popc(tri_votes) >= tri_lanes || node_votes == 0u)) {
-      if (want_tri) done = tr.template triangle_phase<ANY, COUNT>(bvh, pol.anyhit(), &cnt);
+      if (want_tri) done = tr.template triangle_phase<ANY, COUNT>(bvh, pol.anyhit(), &cnt, pol);
       __syncwarp();
     }
     if (have && !done && tr.can_descend()) tr.template node_phase<COUNT>(bvh, &cnt);
+    if (TWO && have && !done && tr.instance_done()) {
+      // the instance's tree is exhausted: back to the instance tree with the world ray
+      float3 wo, wd;
+      pol.world_ray(wo, wd);
+      tr.leave_instance(wo, wd);
+    }
     if (have && (done || tr.finished())) {
       have = false;
       finished = true;

@@ -391,13 +391,12 @@ struct CollapseCounters {
   uint32_t n_tris;
 };
 
-__global__ void k_collapse(uint32_t level_begin, uint32_t level_end, uint32_t* __restrict__ work, int n,
-                           Lbvh t, const float4* __restrict__ wtri, const uint32_t* __restrict__ sorted,
-                           CollapseCounters* __restrict__ counters, Node8* __restrict__ nodes,
-                           float4* __restrict__ tris)
+// one 8-wide node: n8 is built from the binary sub-tree rooted at work[n8]
+__device__ void collapse_node(uint32_t n8, uint32_t* __restrict__ work, int n, const Lbvh& t,
+                              const float4* __restrict__ wtri, const uint32_t* __restrict__ sorted,
+                              CollapseCounters* __restrict__ counters, Node8* __restrict__ nodes,
+                              float4* __restrict__ tris)
 {
-  const uint32_t n8 = level_begin + blockIdx.x * blockDim.x + threadIdx.x;
-  if (n8 >= level_end) return;
   const uint32_t b2 = work[n8];
 
   uint32_t c[8];
@@ -554,6 +553,50 @@ __global__ void k_collapse(uint32_t level_begin, uint32_t level_end, uint32_t* _
     }
   }
   nodes[n8] = out;
+}
+
+// one level of the 8-wide tree per launch (the host reads the node counter between levels)
+__global__ void k_collapse(uint32_t level_begin, uint32_t level_end, uint32_t* __restrict__ work, int n,
+                           Lbvh t, const float4* __restrict__ wtri, const uint32_t* __restrict__ sorted,
+                           CollapseCounters* __restrict__ counters, Node8* __restrict__ nodes,
+                           float4* __restrict__ tris)
+{
+  const uint32_t n8 = level_begin + blockIdx.x * blockDim.x + threadIdx.x;
+  if (n8 >= level_end) return;
+  collapse_node(n8, work, n, t, wtri, sorted, counters, nodes, tris);
+}
+
+// small trees (an instance tree of a few thousand boxes): all levels in ONE launch of one block, which walks the
+// levels itself -- no host round trip per level.  depth_out receives the number of levels.
+constexpr int kCollapseSmallThreads = 256;
+constexpr int kSmallTree = 16384;  // primitives
+__global__ void __launch_bounds__(kCollapseSmallThreads) k_collapse_small(uint32_t* __restrict__ work, int n, Lbvh t,
+                                                                         const float4* __restrict__ wtri,
+                                                                         const uint32_t* __restrict__ sorted,
+                                                                         CollapseCounters* __restrict__ counters,
+                                                                         Node8* __restrict__ nodes, float4* __restrict__ tris,
+                                                                         uint32_t max_nodes, uint32_t* __restrict__ depth_out)
+{
+  __shared__ uint32_t s_begin, s_end;
+  if (threadIdx.x == 0) {
+    s_begin = 0;
+    s_end = 1;
+  }
+  __syncthreads();
+  uint32_t depth = 0;
+  while (s_begin < s_end && s_end <= max_nodes) {
+    for (uint32_t n8 = s_begin + threadIdx.x; n8 < s_end; n8 += blockDim.x)
+      collapse_node(n8, work, n, t, wtri, sorted, counters, nodes, tris);
+    __threadfence_block();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      s_begin = s_end;
+      s_end = counters->n_nodes;
+    }
+    depth++;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *depth_out = depth;
 }
 
 __global__ void k_empty_root(Node8* nodes)
@@ -814,6 +857,19 @@ void build_bvh_with(bool use_ploc, cudaStream_t stream, const float3* d_vertices
   FR_CUDA_CHECK(cudaMemcpyAsync(counters.get(), &init_c, sizeof(init_c), cudaMemcpyHostToDevice, stream));
   FR_CUDA_CHECK(cudaMemcpyAsync(work.get(), &root_id, sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
   uint32_t begin = 0, end = 1, depth = 0;
+  if (n <= kSmallTree) {
+    // instance trees and other small inputs: one launch, one read-back
+    ScratchBuf<uint32_t> d_depth(1);
+    k_collapse_small<<<1, kCollapseSmallThreads, 0, stream>>>(work.get(), n, t, wtri.get(), tri_order, counters.get(), nodes.get(),
+                                                               out.tris.get(), (uint32_t)max_nodes, d_depth.get());
+    FR_CUDA_LAUNCH_CHECK();
+    CollapseCounters h;
+    FR_CUDA_CHECK(cudaMemcpyAsync(&h, counters.get(), sizeof(h), cudaMemcpyDeviceToHost, stream));
+    FR_CUDA_CHECK(cudaMemcpyAsync(&depth, d_depth.get(), sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    FR_CUDA_CHECK(cudaStreamSynchronize(stream));
+    if (h.n_nodes > max_nodes) throw std::runtime_error("bvh collapse: node pool overflow");
+    begin = end = h.n_nodes;
+  }
   while (begin < end) {
     const uint32_t cnt = end - begin;
     k_collapse<<<(cnt + 63) / 64, 64, 0, stream>>>(begin, end, work.get(), n, t, wtri.get(), tri_order,
@@ -848,9 +904,9 @@ void build_bvh_with(bool use_ploc, cudaStream_t stream, const float3* d_vertices
 
 void build_bvh(cudaStream_t stream, const float3* d_vertices, const uint3* d_indices,
                const uint32_t* d_face_submesh, const uint32_t* d_face_flags,
-               const fredholm::Matrix3x4* d_o2w, uint32_t n_faces, DeviceBvh& out)
+               const fredholm::Matrix3x4* d_o2w, uint32_t n_faces, DeviceBvh& out, int builder)
 {
-  const bool ploc = builder_is_ploc();
+  const bool ploc = builder < 0 ? builder_is_ploc() : builder == 1;
   // a 52 M-triangle build uses ~10 GB of temporaries (trim_scratch_pool: what stays cached afterwards)
   struct TrimPool {
     ~TrimPool() { trim_scratch_pool(); }

@@ -307,9 +307,37 @@ int fr_get_accel_info(fr_renderer* r, uint32_t* out3, float* build_ms, uint64_t*
   });
 }
 
+int fr_set_accel_mode(fr_renderer* r, int mode)
+{
+  return guarded([&] {
+    if (mode < 0 || mode > 2) throw std::invalid_argument("fr_set_accel_mode: 0 = auto, 1 = flat, 2 = two-level");
+    r->renderer.set_accel_mode(static_cast<AccelMode>(mode));
+  });
+}
+int fr_get_accel_info2(fr_renderer* r, uint32_t* out5, float* tlas_update_ms)
+{
+  return guarded([&] {
+    const AccelInfo a = r->renderer.get_accel_info();
+    out5[0] = a.two_level ? 1u : 0u;
+    out5[1] = a.n_instances;
+    out5[2] = a.n_meshes;
+    out5[3] = a.n_stored_faces;
+    out5[4] = a.n_nodes;
+    if (tlas_update_ms) *tlas_update_ms = a.tlas_update_ms;
+  });
+}
+
 int fr_get_accel_data(fr_renderer* r, void* nodes80, void* tris48)
 {
   return guarded([&] {
+    if (r->renderer.impl()->two_level) {
+      // two-level structure: the combined arrays -- n_nodes nodes, (instances + stored faces) 48-byte records
+      const frd::TwoLevelBvh& t = r->renderer.impl()->bvh2;
+      FR_CUDA_CHECK(cudaDeviceSynchronize());
+      if (nodes80) FR_CUDA_CHECK(cudaMemcpy(nodes80, t.nodes.get(), sizeof(frd::Node8) * t.n_nodes, cudaMemcpyDeviceToHost));
+      if (tris48) FR_CUDA_CHECK(cudaMemcpy(tris48, t.tris.get(), 48ull * (t.n_instances + t.n_blas_faces), cudaMemcpyDeviceToHost));
+      return;
+    }
     const frd::DeviceBvh& b = r->renderer.impl()->bvh;
     FR_CUDA_CHECK(cudaDeviceSynchronize());
     if (nodes80) FR_CUDA_CHECK(cudaMemcpy(nodes80, b.nodes.get(), sizeof(frd::Node8) * b.n_nodes, cudaMemcpyDeviceToHost));
@@ -325,11 +353,7 @@ int fr_set_time(fr_renderer* r, float time)
 int fr_set_transforms(fr_renderer* r, const float* transforms, uint32_t n_submeshes)
 {
   return guarded([&] {
-    Renderer::Impl* im = r->renderer.impl();
-    if (n_submeshes != im->scene.m_transforms.size()) throw std::runtime_error("transform count mismatch");
-    std::memcpy(im->scene.m_transforms.data(), transforms, sizeof(float) * 16 * n_submeshes);
-    im->upload_transforms();
-    im->build_accel();
+    r->renderer.set_transforms(transforms, n_submeshes);
   });
 }
 

@@ -10,7 +10,11 @@
 #include <chrono>
 #include <cmath>
 #include <cstring>
+#include <algorithm>
+#include <cstdlib>
+#include <map>
 #include <stdexcept>
+#include <thread>
 #include <vector>
 
 #include "lobes.h"
@@ -230,7 +234,119 @@ void Renderer::Impl::upload_scene()
   }
   n_lights = (uint32_t)lights.size();
   if (n_lights) d_lights.upload(lights, stream);
+  find_distinct_meshes();
   upload_transforms();
+}
+
+// Sub-meshes whose triangles have identical object-space positions, in the same order, are copies of one mesh
+// (the reference's glTF path makes one sub-mesh with its own vertex copy per node, scene.cpp:730-822, and so does
+// every instancing exporter): they can share one object-space tree.  128-bit content hash per sub-mesh, computed
+// on all host threads; candidates are grouped by (face count, hash).
+void Renderer::Impl::find_distinct_meshes()
+{
+  const Scene& s = scene;
+  const size_t n_sm = s.m_submesh_offsets.size();
+  struct Key {
+    uint64_t a, b;
+    uint32_t n;
+    bool operator<(const Key& o) const { return n != o.n ? n < o.n : (a != o.a ? a < o.a : b < o.b); }
+  };
+  std::vector<Key> keys(n_sm);
+  auto hash_range = [&](size_t begin, size_t end) {
+    for (size_t sm = begin; sm < end; ++sm) {
+      uint64_t a = 0x9e3779b97f4a7c15ull, b = 0xc2b2ae3d27d4eb4full;
+      const uint32_t off = s.m_submesh_offsets[sm], nf = s.m_submesh_n_faces[sm];
+      for (uint32_t f = 0; f < nf; ++f) {
+        const uint3 idx = s.m_indices[off + f];
+        const uint32_t vid[3] = {idx.x, idx.y, idx.z};
+        for (int k = 0; k < 3; ++k) {
+          uint32_t w[3];
+          std::memcpy(w, &s.m_vertices[vid[k]], 12);
+          for (int c = 0; c < 3; ++c) {
+            a = (a ^ w[c]) * 0x100000001b3ull;
+            a ^= a >> 29;
+            b = (b + w[c]) * 0xff51afd7ed558ccdull;
+            b ^= b >> 32;
+          }
+        }
+      }
+      keys[sm] = Key{a, b, nf};
+    }
+  };
+  const unsigned n_threads = std::max(1u, std::min<unsigned>(std::thread::hardware_concurrency(), (unsigned)n_sm));
+  if (n_threads <= 1 || s.m_indices.size() < (1u << 16)) {
+    hash_range(0, n_sm);
+  } else {
+    // contiguous ranges with about the same number of faces each
+    std::vector<std::thread> th;
+    const size_t total = s.m_indices.size();
+    size_t begin = 0;
+    for (unsigned t = 0; t < n_threads && begin < n_sm; ++t) {
+      const size_t target = total * (t + 1) / n_threads;
+      size_t end = begin;
+      while (end < n_sm && (end == begin || (size_t)s.m_submesh_offsets[end] + s.m_submesh_n_faces[end] <= target)) ++end;
+      if (t + 1 == n_threads) end = n_sm;
+      th.emplace_back(hash_range, begin, end);
+      begin = end;
+    }
+    for (auto& t : th) t.join();
+  }
+  std::map<Key, uint32_t> first;
+  mesh_of_submesh.assign(n_sm, 0);
+  mesh_representative.clear();
+  for (size_t sm = 0; sm < n_sm; ++sm) {
+    auto it = first.find(keys[sm]);
+    if (it == first.end()) {
+      it = first.emplace(keys[sm], (uint32_t)mesh_representative.size()).first;
+      mesh_representative.push_back((uint32_t)sm);
+    }
+    mesh_of_submesh[sm] = it->second;
+  }
+}
+
+bool Renderer::Impl::want_two_level() const
+{
+  if (const char* e = getenv("FRD_ACCEL")) {  // experiments / tests: flat | two_level
+    if (std::strcmp(e, "flat") == 0) return false;
+    if (std::strcmp(e, "two_level") == 0) return true;
+  }
+  if (accel_mode == AccelMode::FLAT) return false;
+  for (uint32_t nf : scene.m_submesh_n_faces)
+    if (nf == 0) return false;  // an empty sub-mesh has no box to place
+  if (accel_mode == AccelMode::TWO_LEVEL) return true;
+  // AUTO: the flat world-space tree is the bit-exact and the faster one, so it stays the choice while it fits;
+  // a scene whose flat tree (128 B per triangle incl. nodes, ~3x that while building) would take more than a
+  // third of the device's memory goes two-level if at least half of its triangles are copies of another sub-mesh
+  size_t stored = 0;
+  for (uint32_t rep : mesh_representative) stored += scene.m_submesh_n_faces[rep];
+  size_t free_b = 0, total_b = 0;
+  if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return false;
+  const size_t flat_build_bytes = scene.m_indices.size() * size_t(3 * 128);
+  return flat_build_bytes > total_b / 3 && 2 * stored <= scene.m_indices.size();
+}
+
+void Renderer::Impl::refresh_accel_info(float build_ms)
+{
+  accel_info = AccelInfo();
+  accel_info.build_ms = build_ms;
+  accel_info.n_faces = (uint32_t)scene.m_indices.size();
+  accel_info.two_level = two_level;
+  if (two_level) {
+    accel_info.n_nodes = bvh2.n_nodes;
+    accel_info.depth = bvh2.depth;
+    accel_info.bytes = bvh2.bytes();
+    accel_info.n_instances = bvh2.n_instances;
+    accel_info.n_meshes = bvh2.n_meshes;
+    accel_info.n_stored_faces = bvh2.n_blas_faces;
+    accel_info.tlas_update_ms = bvh2.tlas_ms;
+  } else {
+    accel_info.n_nodes = bvh.n_nodes;
+    accel_info.depth = bvh.depth;
+    accel_info.bytes = size_t(bvh.n_nodes) * sizeof(frd::Node8) + size_t(bvh.n_faces) * 3 * sizeof(float4);
+    accel_info.n_instances = (uint32_t)scene.m_submesh_offsets.size();
+    accel_info.n_meshes = accel_info.n_instances;
+    accel_info.n_stored_faces = bvh.n_faces;
+  }
 }
 
 void Renderer::Impl::build_accel()
@@ -239,18 +355,53 @@ void Renderer::Impl::build_accel()
   FR_CUDA_CHECK(cudaEventCreate(&e0));
   FR_CUDA_CHECK(cudaEventCreate(&e1));
   FR_CUDA_CHECK(cudaEventRecord(e0, stream));
-  frd::build_bvh(stream, d_vertices.get(), d_indices.get(), d_face_submesh.get(), d_face_flags.get(), d_o2w.get(),
-                 (uint32_t)scene.m_indices.size(), bvh);
+  two_level = want_two_level();
+  if (two_level) {
+    // alpha-test flag of a shared triangle: set if ANY instance of the mesh has an alpha-tested material there
+    // (the any-hit functor looks at the real material of the face that was hit)
+    std::vector<std::vector<uint32_t>> flags(mesh_representative.size());
+    bool any_flag = false;
+    for (size_t sm = 0; sm < scene.m_submesh_offsets.size(); ++sm) {
+      const uint32_t off = scene.m_submesh_offsets[sm], nf = scene.m_submesh_n_faces[sm];
+      for (uint32_t f = 0; f < nf; ++f) {
+        const Material& m = scene.m_materials[scene.m_material_ids[off + f]];
+        if (m.base_color_texture_id >= 0 || m.alpha_texture_id >= 0) {
+          std::vector<uint32_t>& v = flags[mesh_of_submesh[sm]];
+          if (v.empty()) v.assign(nf, 0u);
+          v[f] = 1u;
+          any_flag = true;
+        }
+      }
+    }
+    frd::build_two_level(stream, d_vertices.get(), d_indices.get(), scene.m_submesh_offsets, scene.m_submesh_n_faces,
+                         mesh_of_submesh, mesh_representative, any_flag ? &flags : nullptr, d_o2w.get(), bvh2);
+    bvh = frd::DeviceBvh();  // the flat tree of an earlier build is not kept
+  } else {
+    frd::build_bvh(stream, d_vertices.get(), d_indices.get(), d_face_submesh.get(), d_face_flags.get(), d_o2w.get(),
+                   (uint32_t)scene.m_indices.size(), bvh);
+    bvh2 = frd::TwoLevelBvh();
+  }
   FR_CUDA_CHECK(cudaEventRecord(e1, stream));
   FR_CUDA_CHECK(cudaEventSynchronize(e1));
-  FR_CUDA_CHECK(cudaEventElapsedTime(&accel_info.build_ms, e0, e1));
+  float ms = 0.0f;
+  FR_CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
-  accel_info.n_faces = bvh.n_faces;
-  accel_info.n_nodes = bvh.n_nodes;
-  accel_info.depth = bvh.depth;
-  accel_info.bytes = size_t(bvh.n_nodes) * sizeof(frd::Node8) + size_t(bvh.n_faces) * 3 * sizeof(float4);
+  refresh_accel_info(ms);
   accel_valid = true;
+}
+
+// transforms changed: the instance tree follows (two-level), or the whole world-space tree is rebuilt (flat)
+void Renderer::Impl::update_accel_after_transform_change()
+{
+  upload_transforms();
+  if (two_level && bvh2.n_instances == scene.m_transforms.size() && bvh2.n_instances > 0) {
+    frd::update_tlas(stream, d_o2w.get(), bvh2);
+    refresh_accel_info(accel_info.build_ms);
+    accel_valid = true;
+  } else {
+    build_accel();
+  }
 }
 
 frd::SceneView Renderer::Impl::view(const float3& bg_color) const
@@ -270,9 +421,15 @@ frd::SceneView Renderer::Impl::view(const float3& bg_color) const
   v.w2o = d_w2o.get();
   v.lights = d_lights.get();
   v.n_lights = n_lights;
-  v.bvh = bvh.view();
-  v.bounds_lo = make_float3(bvh.bounds_lo[0], bvh.bounds_lo[1], bvh.bounds_lo[2]);
-  v.bounds_hi = make_float3(bvh.bounds_hi[0], bvh.bounds_hi[1], bvh.bounds_hi[2]);
+  if (two_level) {
+    v.bvh = bvh2.view(d_w2o.get());
+    v.bounds_lo = make_float3(bvh2.bounds_lo[0], bvh2.bounds_lo[1], bvh2.bounds_lo[2]);
+    v.bounds_hi = make_float3(bvh2.bounds_hi[0], bvh2.bounds_hi[1], bvh2.bounds_hi[2]);
+  } else {
+    v.bvh = bvh.view();
+    v.bounds_lo = make_float3(bvh.bounds_lo[0], bvh.bounds_lo[1], bvh.bounds_lo[2]);
+    v.bounds_hi = make_float3(bvh.bounds_hi[0], bvh.bounds_hi[1], bvh.bounds_hi[2]);
+  }
   v.has_dir_light = has_dir_light ? 1 : 0;
   v.dir_light = dir_light;
   if (has_dir_light) {
@@ -365,8 +522,31 @@ void Renderer::set_time(float time)
   const bool moved = before.size() != after.size() ||
                      (!after.empty() && std::memcmp(before.data(), after.data(), sizeof(mat4) * after.size()) != 0);
   if (!moved && m_impl->accel_valid) return;
-  m_impl->upload_transforms();
-  m_impl->build_accel();
+  if (!m_impl->accel_valid) {
+    m_impl->upload_transforms();
+    m_impl->build_accel();
+  } else {
+    m_impl->update_accel_after_transform_change();
+  }
+}
+
+void Renderer::set_accel_mode(AccelMode mode)
+{
+  if (mode != m_impl->accel_mode) m_impl->accel_valid = false;
+  m_impl->accel_mode = mode;
+}
+
+void Renderer::set_transforms(const float* transforms16, uint32_t n_submeshes)
+{
+  FR_CUDA_CHECK(cudaSetDevice(m_impl->device));
+  if (n_submeshes != m_impl->scene.m_transforms.size()) throw std::runtime_error("transform count mismatch");
+  std::memcpy(m_impl->scene.m_transforms.data(), transforms16, sizeof(float) * 16 * n_submeshes);
+  if (!m_impl->accel_valid) {
+    m_impl->upload_transforms();
+    m_impl->build_accel();
+  } else {
+    m_impl->update_accel_after_transform_change();
+  }
 }
 
 void Renderer::set_directional_light(const float3& le, const float3& dir, float angle)

@@ -45,9 +45,18 @@ struct Renderer::Impl {
   bool has_hosek = false;
   frd::HosekSky hosek;
 
-  frd::DeviceBvh bvh;
+  frd::DeviceBvh bvh;           // flat world-space tree
+  frd::TwoLevelBvh bvh2;        // per-mesh trees + instance tree
+  bool two_level = false;       // which of the two the last build produced
+  AccelMode accel_mode = AccelMode::AUTO;
   bool accel_valid = false;
   AccelInfo accel_info;
+  // distinct meshes of the scene (sub-meshes with identical triangle positions share one): filled by upload_scene
+  std::vector<uint32_t> mesh_of_submesh, mesh_representative;
+  void find_distinct_meshes();
+  bool want_two_level() const;
+  void refresh_accel_info(float build_ms);
+  void update_accel_after_transform_change();
 
   std::unique_ptr<frd::Integrator> integrator;
 

@@ -26,6 +26,9 @@ constexpr int kBlock = 128;
 #ifndef FRD_TRACE_BLOCKS
 #define FRD_TRACE_BLOCKS 8  // resident CTAs per SM: 64 registers per thread
 #endif
+#ifndef FRD_TRACE_BLOCKS_TWO
+#define FRD_TRACE_BLOCKS_TWO 6  // two-level instantiations (instance index, stack floor, record index): 80 registers
+#endif
 
 // alpha cut-out: candidate is ignored if base-colour alpha or the alpha map is < 0.5
 struct AlphaTest {
@@ -82,6 +85,11 @@ struct ClosestPolicy {
     tmin = 0.0f;
     tmax = 1e9f;
   }
+  FR_D void world_ray(float3& o, float3& d) const
+  {
+    o = f3(wb.ray_o[slot]);
+    d = f3(wb.ray_d[slot]);
+  }
   FR_D void retire(bool has, const HitRecord& h, const TraceCounters& cnt)
   {
     count_retire<COUNT>(wb.ctl, 0, has, cnt);
@@ -106,13 +114,13 @@ struct ClosestPolicy {
   }
 };
 
-template <bool COUNT>
-__global__ void __launch_bounds__(kBlock, FRD_TRACE_BLOCKS) k_trace_closest(SceneView sc, WaveBuffers wb, uint32_t depth, int refill, int tri_lanes,
+template <bool COUNT, bool TWO>
+__global__ void __launch_bounds__(kBlock, TWO ? FRD_TRACE_BLOCKS_TWO : FRD_TRACE_BLOCKS) k_trace_closest(SceneView sc, WaveBuffers wb, uint32_t depth, int refill, int tri_lanes,
                                                              const uint32_t* order)
 {
   FR_DECLARE_STACK();
   ClosestPolicy<COUNT> pol{sc, wb, order ? order : wb.queue[depth & 1u], depth, 0u};
-  trace_queue<false, COUNT>(sc.bvh, pol, &wb.ctl->cursor[0], wb.ctl->n[Q_CUR], stack_column, kBlock, refill, tri_lanes);
+  trace_queue<false, COUNT, TWO>(sc.bvh, pol, &wb.ctl->cursor[0], wb.ctl->n[Q_CUR], stack_column, kBlock, refill, tri_lanes);
 }
 
 // ---- visibility rays: any hit; an unoccluded ray adds its contribution ----------------------
@@ -124,10 +132,12 @@ struct ShadowPolicy {
   const uint32_t* order;
   uint32_t path;
   float3 c;
+  uint32_t record;  // index of the ray record (read again by world_ray in two-level mode only)
   FR_D AlphaTest anyhit() const { return AlphaTest{&sc}; }
   FR_D void load(uint32_t item, float3& o, float3& d, float& tmin, float& tmax)
   {
     if (order) item = order[item];
+    record = item;
     const float4 r0 = __ldcs(q + 3ull * item), r1 = __ldcs(q + 3ull * item + 1), r2 = __ldcs(q + 3ull * item + 2);
     o = f3(r0);
     d = f3(r1);
@@ -135,6 +145,11 @@ struct ShadowPolicy {
     tmax = r0.w;
     path = __float_as_uint(r1.w);
     c = f3(r2);
+  }
+  FR_D void world_ray(float3& o, float3& d) const
+  {
+    o = f3(q[3ull * record]);
+    d = f3(q[3ull * record + 1]);
   }
   FR_D void retire(bool has, const HitRecord& h, const TraceCounters& cnt)
   {
@@ -150,15 +165,15 @@ struct ShadowPolicy {
   }
 };
 
-template <bool COUNT>
-__global__ void __launch_bounds__(kBlock, FRD_TRACE_BLOCKS) k_trace_shadow(SceneView sc, WaveBuffers wb, int which, int refill, int tri_lanes,
+template <bool COUNT, bool TWO>
+__global__ void __launch_bounds__(kBlock, TWO ? FRD_TRACE_BLOCKS_TWO : FRD_TRACE_BLOCKS) k_trace_shadow(SceneView sc, WaveBuffers wb, int which, int refill, int tri_lanes,
                                                             const uint32_t* order)
 {
   FR_DECLARE_STACK();
   // which == 3: the MIS-ray queue holding visibility records (scenes without emitters, shade.cu)
   ShadowPolicy<COUNT> pol{sc, wb, reinterpret_cast<const float4*>(which < 3 ? wb.shadow[which] : (const ShadowRay*)wb.light), order,
-                   0u, f3(0.f)};
-  trace_queue<true, COUNT>(sc.bvh, pol, &wb.ctl->cursor[2 + which], wb.ctl->n[Q_SHADOW0 + which], stack_column, kBlock,
+                   0u, f3(0.f), 0u};
+  trace_queue<true, COUNT, TWO>(sc.bvh, pol, &wb.ctl->cursor[2 + which], wb.ctl->n[Q_SHADOW0 + which], stack_column, kBlock,
                            refill, tri_lanes);
 }
 
@@ -185,6 +200,11 @@ struct LightPolicy {
     path = __float_as_uint(r1.w);
     w = f3(r2);
     cos_wi = r2.w;
+  }
+  FR_D void world_ray(float3& ro, float3& rd) const
+  {
+    ro = o;
+    rd = d;
   }
   FR_D void retire(bool has, const HitRecord& h, const TraceCounters& cnt)
   {
@@ -232,13 +252,13 @@ struct LightPolicy {
 
 // (scenes without any emissive face never get here: their MIS rays are visibility rays with
 // the sky contribution precomputed by the shade stage, traced by k_trace_shadow)
-template <bool COUNT>
-__global__ void __launch_bounds__(kBlock, FRD_TRACE_BLOCKS) k_trace_light(SceneView sc, WaveBuffers wb, int refill, int tri_lanes,
+template <bool COUNT, bool TWO>
+__global__ void __launch_bounds__(kBlock, TWO ? FRD_TRACE_BLOCKS_TWO : FRD_TRACE_BLOCKS) k_trace_light(SceneView sc, WaveBuffers wb, int refill, int tri_lanes,
                                                            const uint32_t* order)
 {
   FR_DECLARE_STACK();
   LightPolicy<COUNT> pol{sc, wb, reinterpret_cast<const float4*>(wb.light), order, f3(0.f), f3(0.f), f3(0.f), 0.f, 0.f, 0u};
-  trace_queue<false, COUNT>(sc.bvh, pol, &wb.ctl->cursor[5], wb.ctl->n[Q_LIGHT], stack_column, kBlock, refill, tri_lanes);
+  trace_queue<false, COUNT, TWO>(sc.bvh, pol, &wb.ctl->cursor[5], wb.ctl->n[Q_LIGHT], stack_column, kBlock, refill, tri_lanes);
 }
 
 // stand-alone batch query for the parity tests: same driver and phases as the stages above
@@ -259,6 +279,11 @@ struct BatchPolicy {
     d = f3(rays[6ull * i + 3], rays[6ull * i + 4], rays[6ull * i + 5]);
     tmin = tmin0;
     tmax = tmax0;
+  }
+  FR_D void world_ray(float3& o, float3& d) const
+  {
+    o = f3(rays[6ull * i], rays[6ull * i + 1], rays[6ull * i + 2]);
+    d = f3(rays[6ull * i + 3], rays[6ull * i + 4], rays[6ull * i + 5]);
   }
   FR_D void retire(bool has, const HitRecord& h, const TraceCounters& cnt)
   {
@@ -281,6 +306,7 @@ struct BatchPolicy {
   }
 };
 
+template <bool TWO>
 __global__ void __launch_bounds__(kBlock) k_trace_batch(SceneView sc, const uint32_t* __restrict__ submesh_offsets,
                                                         const float* __restrict__ rays, uint32_t n, float tmin,
                                                         float tmax, uint32_t* __restrict__ out_id,
@@ -289,10 +315,11 @@ __global__ void __launch_bounds__(kBlock) k_trace_batch(SceneView sc, const uint
 {
   FR_DECLARE_STACK();
   BatchPolicy pol{sc, submesh_offsets, rays, tmin, tmax, out_id, out_tuv, counters, 0u};
-  trace_queue<false, true>(sc.bvh, pol, cursor, n, stack_column, kBlock, refill, tri_lanes);
+  trace_queue<false, true, TWO>(sc.bvh, pol, cursor, n, stack_column, kBlock, refill, tri_lanes);
 }
 
 int g_grid_closest = 0, g_grid_shadow = 0, g_grid_light = 0;
+int g_grid_closest2 = 0, g_grid_shadow2 = 0, g_grid_light2 = 0;  // two-level instantiations
 
 // idle lanes per warp that trigger a refill (tunable for experiments: FRD_REFILL_LANES)
 int env_int(const char* name, int fallback)
@@ -341,24 +368,36 @@ void set_traversal_counting(bool on) { g_count_traversal = on; }
 void launch_trace_closest(cudaStream_t s, const SceneView& sc, const WaveBuffers& wb, uint32_t depth,
                           const uint32_t* order)
 {
-  if (!g_grid_closest) g_grid_closest = persistent_grid(reinterpret_cast<const void*>(k_trace_closest<false>), kBlock);
   const int refill = depth == 0 ? refill_lanes_coherent() : refill_lanes();
+  if (sc.bvh.instances) {
+    if (!g_grid_closest2) g_grid_closest2 = persistent_grid(reinterpret_cast<const void*>(k_trace_closest<false, true>), kBlock);
+    k_trace_closest<false, true><<<g_grid_closest2, kBlock, 0, s>>>(sc, wb, depth, refill, tri_lanes_closest(), order);
+    FR_CUDA_LAUNCH_CHECK();
+    return;
+  }
+  if (!g_grid_closest) g_grid_closest = persistent_grid(reinterpret_cast<const void*>(k_trace_closest<false, false>), kBlock);
   if (g_count_traversal)
-    k_trace_closest<true><<<g_grid_closest, kBlock, 0, s>>>(sc, wb, depth, refill, tri_lanes_closest(), order);
+    k_trace_closest<true, false><<<g_grid_closest, kBlock, 0, s>>>(sc, wb, depth, refill, tri_lanes_closest(), order);
   else
-    k_trace_closest<false><<<g_grid_closest, kBlock, 0, s>>>(sc, wb, depth, refill, tri_lanes_closest(), order);
+    k_trace_closest<false, false><<<g_grid_closest, kBlock, 0, s>>>(sc, wb, depth, refill, tri_lanes_closest(), order);
   FR_CUDA_LAUNCH_CHECK();
 }
 
 void launch_trace_shadow(cudaStream_t s, const SceneView& sc, const WaveBuffers& wb, int which, const uint32_t* order,
                          bool coherent)
 {
-  if (!g_grid_shadow) g_grid_shadow = persistent_grid(reinterpret_cast<const void*>(k_trace_shadow<false>), kBlock);
   const int refill = coherent ? refill_lanes_coherent() : refill_lanes();
+  if (sc.bvh.instances) {
+    if (!g_grid_shadow2) g_grid_shadow2 = persistent_grid(reinterpret_cast<const void*>(k_trace_shadow<false, true>), kBlock);
+    k_trace_shadow<false, true><<<g_grid_shadow2, kBlock, 0, s>>>(sc, wb, which, refill, tri_lanes_any(), order);
+    FR_CUDA_LAUNCH_CHECK();
+    return;
+  }
+  if (!g_grid_shadow) g_grid_shadow = persistent_grid(reinterpret_cast<const void*>(k_trace_shadow<false, false>), kBlock);
   if (g_count_traversal)
-    k_trace_shadow<true><<<g_grid_shadow, kBlock, 0, s>>>(sc, wb, which, refill, tri_lanes_any(), order);
+    k_trace_shadow<true, false><<<g_grid_shadow, kBlock, 0, s>>>(sc, wb, which, refill, tri_lanes_any(), order);
   else
-    k_trace_shadow<false><<<g_grid_shadow, kBlock, 0, s>>>(sc, wb, which, refill, tri_lanes_any(), order);
+    k_trace_shadow<false, false><<<g_grid_shadow, kBlock, 0, s>>>(sc, wb, which, refill, tri_lanes_any(), order);
   FR_CUDA_LAUNCH_CHECK();
 }
 
@@ -368,11 +407,17 @@ void launch_trace_light(cudaStream_t s, const SceneView& sc, const WaveBuffers& 
     launch_trace_shadow(s, sc, wb, 3, order, false);
     return;
   }
-  if (!g_grid_light) g_grid_light = persistent_grid(reinterpret_cast<const void*>(k_trace_light<false>), kBlock);
+  if (sc.bvh.instances) {
+    if (!g_grid_light2) g_grid_light2 = persistent_grid(reinterpret_cast<const void*>(k_trace_light<false, true>), kBlock);
+    k_trace_light<false, true><<<g_grid_light2, kBlock, 0, s>>>(sc, wb, refill_lanes(), tri_lanes_closest(), order);
+    FR_CUDA_LAUNCH_CHECK();
+    return;
+  }
+  if (!g_grid_light) g_grid_light = persistent_grid(reinterpret_cast<const void*>(k_trace_light<false, false>), kBlock);
   if (g_count_traversal)
-    k_trace_light<true><<<g_grid_light, kBlock, 0, s>>>(sc, wb, refill_lanes(), tri_lanes_closest(), order);
+    k_trace_light<true, false><<<g_grid_light, kBlock, 0, s>>>(sc, wb, refill_lanes(), tri_lanes_closest(), order);
   else
-    k_trace_light<false><<<g_grid_light, kBlock, 0, s>>>(sc, wb, refill_lanes(), tri_lanes_closest(), order);
+    k_trace_light<false, false><<<g_grid_light, kBlock, 0, s>>>(sc, wb, refill_lanes(), tri_lanes_closest(), order);
   FR_CUDA_LAUNCH_CHECK();
 }
 
@@ -388,10 +433,17 @@ void trace_batch_closest(const SceneView& sc, const uint32_t* d_submesh_offsets,
   d_cnt.zero();
   d_cursor.zero();
   FR_CUDA_CHECK(cudaMemcpy(d_rays.get(), rays_host, sizeof(float) * 6ull * n, cudaMemcpyHostToDevice));
-  const int grid = std::min<int>((n + kBlock - 1) / kBlock, persistent_grid(reinterpret_cast<const void*>(k_trace_batch), kBlock));
-  k_trace_batch<<<grid, kBlock>>>(sc, d_submesh_offsets, d_rays.get(), n, tmin, tmax, d_id.get(), d_tuv.get(),
-                                  counters2_host ? d_cnt.get() : nullptr, d_cursor.get(), refill_lanes(),
-                                  tri_lanes_closest());
+  if (sc.bvh.instances) {
+    const int grid = std::min<int>((n + kBlock - 1) / kBlock, persistent_grid(reinterpret_cast<const void*>(k_trace_batch<true>), kBlock));
+    k_trace_batch<true><<<grid, kBlock>>>(sc, d_submesh_offsets, d_rays.get(), n, tmin, tmax, d_id.get(), d_tuv.get(),
+                                          counters2_host ? d_cnt.get() : nullptr, d_cursor.get(), refill_lanes(),
+                                          tri_lanes_closest());
+  } else {
+    const int grid = std::min<int>((n + kBlock - 1) / kBlock, persistent_grid(reinterpret_cast<const void*>(k_trace_batch<false>), kBlock));
+    k_trace_batch<false><<<grid, kBlock>>>(sc, d_submesh_offsets, d_rays.get(), n, tmin, tmax, d_id.get(), d_tuv.get(),
+                                           counters2_host ? d_cnt.get() : nullptr, d_cursor.get(), refill_lanes(),
+                                           tri_lanes_closest());
+  }
   FR_CUDA_LAUNCH_CHECK();
   FR_CUDA_CHECK(cudaMemcpy(out_id_host, d_id.get(), sizeof(uint32_t) * 2ull * n, cudaMemcpyDeviceToHost));
   FR_CUDA_CHECK(cudaMemcpy(out_tuv_host, d_tuv.get(), sizeof(float) * 3ull * n, cudaMemcpyDeviceToHost));

@@ -57,7 +57,19 @@ struct AccelInfo {
   uint32_t depth = 0;
   float build_ms = 0.0f;
   size_t bytes = 0;
+  // two-level structure (instanced scenes): distinct meshes, triangles actually stored, time of the last
+  // instance-tree update (set_time / transform change)
+  bool two_level = false;
+  uint32_t n_instances = 0, n_meshes = 0, n_stored_faces = 0;
+  float tlas_update_ms = 0.0f;
 };
+
+// Acceleration-structure layout (extension).  FLAT: every instance's triangles in world space in ONE tree (fastest
+// traversal; a transform change rebuilds it).  TWO_LEVEL: one object-space tree per distinct mesh + an instance
+// tree, like the reference's GAS + IAS (renderer.h:434-552); a transform change only rebuilds the instance tree.
+// AUTO: FLAT (bit-exact against the oracle, fastest) unless building it would take more than a third of the
+// device's memory and at least half of the scene's triangles are copies of another sub-mesh.
+enum class AccelMode : int { AUTO = 0, FLAT = 1, TWO_LEVEL = 2 };
 
 class Renderer
 {
@@ -81,6 +93,10 @@ class Renderer
   void build_gas();
   void build_ias();
   void set_time(float time);
+  void set_accel_mode(AccelMode mode);  // extension; takes effect at the next build_gas()
+  // extension: replace the sub-mesh transforms (column-major 4x4 each) and bring the acceleration structure up to
+  // date -- an instance-tree update in TWO_LEVEL mode, a rebuild in FLAT mode
+  void set_transforms(const float* transforms16, uint32_t n_submeshes);
 
   // ---- lights / sky ----
   void set_directional_light(const float3& le, const float3& dir, float angle);

@@ -1,0 +1,251 @@
+"""Two-level acceleration structure (csrc/accel.cu, bvh.cuh TWO = true): one object-space tree per DISTINCT mesh
++ an instance tree, the B200 counterpart of the reference's GAS + IAS (renderer.h:434-552) and of its IAS
+rebuild in set_time (renderer.h:614-640).  Rays are taken to object space at an instance, so t / u / v are no
+longer bit-identical to the world-space oracle: the bar is the north star's -- ids on >= 99.99 % of the rays,
+t to 1e-5 -- plus image gates; the flat tree (bit-exact) stays the default for scenes without instancing."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import rel_mse
+from fredholm_b200 import Camera, DeviceLayers, Renderer, api, make_material, scenes
+from fredholm_b200.scenes import _assemble, _quad
+
+pytestmark = pytest.mark.gpu
+MISS = 0xffffffff
+NT = os.cpu_count() or 1
+
+
+def instanced_camera():
+    c = scenes.INSTANCED_CAMERA
+    return Camera(api.camera_walk(c["origin"], 0.0, 100.0, 0, 0.0), c["fov"], c["F"], c["focus"])
+
+
+def random_rays(n, seed, lo, hi, ylo, yhi):
+    rng = np.random.default_rng(seed)
+    o = rng.uniform(lo, hi, (n, 3)).astype(np.float32)
+    o[:, 1] = rng.uniform(ylo, yhi, n)
+    d = rng.normal(size=(n, 3)).astype(np.float32)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    return np.concatenate([o, d], 1)
+
+
+def agree(rays, ids_a, tuv_a, ids_b, tuv_b, frac=0.9999):
+    """ids identical on >= 99.99 % of the rays; t to 1e-5 RELATIVE TO THE RAY'S COORDINATES: taking a ray to object
+    space rounds its origin at the magnitude of the world coordinates (|o| 2^-24 per operation), so a hit a few
+    units from an origin 150 units out cannot be better than ~1e-5 absolute -- the same holds for OptiX instances.
+    Measured on camera rays: max relative error 1.6e-6, instances with the identity transform bit-exact."""
+    same = (ids_a == ids_b).all(axis=1)
+    assert same.mean() >= frac, same.mean()
+    hit = same & (ids_a[:, 0] != MISS)
+    assert hit.sum() > 100
+    scale = np.maximum(np.abs(tuv_b[hit, 0]), np.abs(rays[hit, :3]).max(axis=1))
+    err_t = np.abs(tuv_a[hit, 0] - tuv_b[hit, 0]) / scale
+    # 99.9 % within 1e-5; the rest are grazing hits, where the same rounding of the origin is divided by the cosine
+    # between ray and surface (measured max 3.8e-5 on 100 k random rays)
+    assert np.quantile(err_t, 0.999) <= 1e-5 and err_t.max() <= 1e-3, (np.quantile(err_t, 0.999), err_t.max())
+    # barycentrics: the same position error divided by the triangle's edge length (0.03 units for the 16 K-triangle
+    # blobs of config 4 seen from 300 units away: 4e-3 at the 99.99th percentile) -- a sanity bound only
+    err_uv = np.abs(tuv_a[hit, 1:] - tuv_b[hit, 1:])
+    assert np.quantile(err_uv, 0.9999) <= 1e-2 and err_uv.max() <= 0.1, (np.quantile(err_uv, 0.9999), err_uv.max())
+    return same.mean()
+
+
+def test_instanced_scene_two_level_matches_flat_and_oracle(oracle):
+    W, H = 480, 270
+    s = scenes.instanced_scene(n_instances=300, mesh_res=(24, 12), terrain_res=64)
+    cam = instanced_camera()
+    flat, two = Renderer(0), Renderer(0)
+    two.set_accel_mode("two_level")             # AUTO keeps the (bit-exact) flat tree while it fits the device
+    for r in (flat, two):
+        r.set_scene(s)
+        r.build_accel()
+        r.set_resolution(W, H)
+    a, b = flat.accel_info(), two.accel_info()
+    assert not a["two_level"] and b["two_level"]
+    assert b["n_instances"] == 301 and b["n_meshes"] == 2
+    assert b["n_stored_faces"] == 2 * 64 * 64 + 2 * 24 * 12 and b["n_faces"] == s.n_faces
+    assert b["bytes"] < a["bytes"] / 10
+    oracle.set_scene(s)
+    oracle.build_accel()
+    oracle.set_resolution(W, H)
+    n_cam = W * H
+    rays = np.concatenate([oracle.primary_rays(cam, 0).reshape(-1, 6), random_rays(100000, 3, -150, 150, 5, 30)])
+    ids_f, tuv_f = flat.trace_closest(rays)
+    ids_t, tuv_t = two.trace_closest(rays)
+    ids_o, tuv_o = oracle.trace_closest(rays)
+    assert np.array_equal(ids_f, ids_o)                       # the flat tree is the bit-exact one
+    agree(rays, ids_t, tuv_t, ids_o, tuv_o)
+    # north-star level 2 on the camera rays: closest-hit t to 1e-5 relative, every ray
+    cam_hit = (ids_o[:n_cam, 0] != MISS) & (ids_t[:n_cam] == ids_o[:n_cam]).all(axis=1)
+    assert np.allclose(tuv_t[:n_cam][cam_hit, 0], tuv_o[:n_cam][cam_hit, 0], rtol=1e-5, atol=0)
+    hit = ids_t[:, 0] != MISS
+    assert len(np.unique(ids_t[hit, 0])) > 100 and ids_t[hit, 1].max() < 2 * 64 * 64
+    # images: closest-hit, any-hit (sky NEE as visibility rays) and depth-16 diffuse transport through both structures
+    imgs = {}
+    for name, r in (("flat", flat), ("two", two)):
+        lay = DeviceLayers(W, H, names=("beauty", "depth"))
+        r.render(cam, (1, 1, 1), lay, 16, 16)
+        r.wait()
+        imgs[name] = (lay.download("beauty"), lay.download("depth"))
+        lay.free()
+    ref, _ = oracle.render_canonical(cam, (1, 1, 1), 16, 16, n_threads=NT)
+    assert rel_mse(imgs["two"][0][..., :3], ref["beauty"][..., :3]) <= 1e-3
+    assert rel_mse(imgs["two"][0][..., :3], imgs["flat"][0][..., :3]) <= 1e-3
+    assert np.isclose(imgs["two"][1], imgs["flat"][1], rtol=1e-5, atol=1e-6).mean() >= 0.9999
+    st = two.statistics()
+    assert st["rays_shadow"] > 0 and st["rays_radiance"] > W * H * 16
+    flat.close()
+    two.close()
+
+
+def test_moving_an_instance_updates_only_the_instance_tree(oracle):
+    s = scenes.instanced_scene(n_instances=300, mesh_res=(24, 12), terrain_res=64)
+    r = Renderer(0)
+    r.set_accel_mode("two_level")
+    r.set_scene(s)
+    r.build_accel()
+    assert r.accel_info()["two_level"]
+    tr = s.transforms.copy().reshape(-1, 4, 4)       # column-major: tr[i, col, row]
+    tr[7, 3, :3] += (11.0, 9.0, -6.0)                # instance 7 flies away
+    tr[150, 0, 0] *= 1.8                             # instance 150 is stretched along x
+    for _ in range(3):
+        r.set_transforms(tr.reshape(-1, 16))
+    info = r.accel_info()
+    assert info["two_level"] and 0.0 < info["tlas_update_ms"] < 0.5, info   # no triangle is touched
+    s2 = scenes.SceneArrays(**{k: getattr(s, k) for k in ("vertices", "normals", "texcoords", "indices", "material_ids",
+                                                           "materials", "submesh_offsets", "submesh_n_faces", "instance_ids")},
+                            transforms=tr.reshape(-1, 16))
+    oracle.set_scene(s2)
+    oracle.build_accel()
+    rays = random_rays(200000, 9, -150, 150, 5, 40)
+    ids_t, tuv_t = r.trace_closest(rays)
+    ids_o, tuv_o = oracle.trace_closest(rays)
+    agree(rays, ids_t, tuv_t, ids_o, tuv_o)
+    assert (ids_t[:, 0] == 7).sum() > 0 and (ids_t[:, 0] == 150).sum() > 0
+    # and back: the structure follows the transforms, not the history
+    r.set_transforms(s.transforms)
+    oracle.set_scene(s)
+    oracle.build_accel()
+    agree(rays, *r.trace_closest(rays), *oracle.trace_closest(rays))
+    r.close()
+
+
+def test_alpha_cutouts_and_area_lights_through_instances(oracle):
+    """Any-hit alpha test and emitter lookup use the GLOBAL face a shared triangle stands for: four copies of a
+    perforated wall with different materials (one of them not perforated) in front of an emissive panel."""
+    tex = np.zeros((16, 16, 4), np.uint8)
+    tex[..., :3] = 200
+    yy, xx = np.mgrid[0:16, 0:16]
+    tex[..., 3] = np.where((xx // 4 + yy // 4) % 2 == 0, 255, 0)
+    holes = make_material(base_color=(0.8, 0.8, 0.8), base_color_texture_id=0)
+    solid = make_material(base_color=(0.8, 0.3, 0.2))
+    lamp = make_material(base_color=(0, 0, 0), emission=1.0, emission_color=(6.0, 5.0, 4.0))
+    floor = make_material(base_color=(0.5, 0.5, 0.5))
+    wall = _quad((-0.5, 0, 0), (0.5, 0, 0), (0.5, 1, 0), (-0.5, 1, 0))
+    shapes = [[(t, 0) for t in wall], [(t, 0) for t in wall], [(t, 1) for t in wall], [(t, 0) for t in wall],
+              [(t, 2) for t in _quad((-3, 0.2, -1.0), (3, 0.2, -1.0), (3, 1.8, -1.0), (-3, 1.8, -1.0))],
+              [(t, 3) for t in _quad((-4, 0, -2), (4, 0, -2), (4, 0, 3), (-4, 0, 3))]]
+    s = _assemble(shapes, [holes, solid, lamp, floor])
+    s.textures = [(tex, True)]
+    tr = np.tile(np.eye(4, dtype=np.float32).reshape(1, 16), (len(shapes), 1)).reshape(-1, 4, 4)
+    for i, x in enumerate((-1.8, -0.6, 0.6, 1.8)):
+        tr[i, 3, 0] = x
+        tr[i, 1, 1] = 1.0 + 0.2 * i
+    s.transforms = tr.reshape(-1, 16)
+    s.instance_ids = np.repeat(np.arange(len(shapes), dtype=np.uint32), 2)
+    W, H = 96, 64
+    cam = Camera(api.camera_walk((0.0, 1.0, 3.2), 0.0, 0.0, 0, 0.0), np.deg2rad(70.0), 100.0, 10000.0)
+    r = Renderer(0)
+    r.set_accel_mode("two_level")
+    r.set_scene(s)
+    r.build_accel()
+    info = r.accel_info()
+    assert info["two_level"] and info["n_meshes"] == 3 and info["n_instances"] == 6   # the four walls share one mesh
+    r.set_resolution(W, H)
+    lay = DeviceLayers(W, H)
+    r.render(cam, (0.2, 0.2, 0.2), lay, 16, 5)
+    r.wait()
+    oracle.set_scene(s)
+    oracle.build_accel()
+    oracle.set_resolution(W, H)
+    ref, _ = oracle.render_canonical(cam, (0.2, 0.2, 0.2), 16, 5, n_threads=NT)
+    d_g, d_o = lay.download("depth"), ref["depth"]
+    assert np.isclose(d_g, d_o, rtol=1e-5, atol=1e-6).mean() >= 0.999
+    assert len(np.unique(np.round(d_o, 3))) > 20
+    assert rel_mse(lay.download("beauty")[..., :3], ref["beauty"][..., :3]) <= 1e-3
+    assert rel_mse(lay.download("albedo")[..., :3], ref["albedo"][..., :3]) <= 2e-4
+    st = r.statistics()
+    assert st["rays_light"] > 0 and st["rays_shadow"] > 0
+    r.close()
+
+
+def test_auto_mode_keeps_the_flat_tree():
+    r = Renderer(0)
+    r.set_scene(scenes.standard_surface_scene(32, 16, sphere_res=(8, 4)))
+    r.build_accel()
+    info = r.accel_info()
+    assert not info["two_level"] and info["n_meshes"] == info["n_instances"]
+    # 300 copies of one mesh, but the flat tree fits the device many times over: still flat (bit-exact)
+    r.set_scene(scenes.instanced_scene(n_instances=300, mesh_res=(24, 12), terrain_res=64))
+    r.build_accel()
+    assert not r.accel_info()["two_level"]
+    r.close()
+
+
+@pytest.mark.timeout(900)
+def test_c4_full_size_two_level(capsys):
+    """BASELINE config 4 at full size: 52 428 800 triangles in 3073 instances of 2 distinct meshes."""
+    W, H = 1920, 1080
+    s = scenes.instanced_scene()
+    cam = instanced_camera()
+    two, flat = Renderer(0), Renderer(0)
+    flat.set_accel_mode("flat")
+    two.set_accel_mode("two_level")
+    two.set_scene(s)
+    two.build_accel()
+    info = two.accel_info()
+    assert info["two_level"] and info["n_meshes"] == 2 and info["n_instances"] == 3073
+    assert info["n_stored_faces"] == 2 * 1024 * 1024 + 16384
+    assert info["bytes"] < 1e9, info["bytes"]                      # flat: 3.1 GB
+    two.set_resolution(W, H)
+    rays = np.concatenate([two.primary_rays(cam, 0).reshape(-1, 6), random_rays(200000, 5, -150, 150, 12, 30)])
+    ids_t, tuv_t = two.trace_closest(rays)
+    flat.set_scene(s)
+    flat.build_accel()
+    ids_f, tuv_f = flat.trace_closest(rays)
+    frac = agree(rays, ids_t, tuv_t, ids_f, tuv_f)
+    # one instance moves: instance-tree update only
+    tr = s.transforms.copy().reshape(-1, 4, 4)
+    tr[1234, 3, 1] += 25.0
+    for _ in range(3):
+        two.set_transforms(tr.reshape(-1, 16))
+    upd = two.accel_info()["tlas_update_ms"]
+    assert upd < 0.5, upd
+    # throughput of both structures on the config's own workload (16 spp, depth 16, white background)
+    out = {}
+    two.set_transforms(s.transforms)
+    for name, r in (("two_level", two), ("flat", flat)):
+        r.set_resolution(W, H)
+        lay = DeviceLayers(W, H, names=("beauty",))
+        r.render(cam, (1, 1, 1), lay, 4, 16)
+        r.wait()
+        r.reset_statistics()
+        e0 = r.record_event()
+        lay.clear()
+        r.init_render_states()
+        r.render(cam, (1, 1, 1), lay, 16, 16)
+        e1 = r.record_event()
+        r.wait()
+        ms = api.event_elapsed_ms(e0, e1)
+        out[name] = (ms, r.statistics()["paths"] / ms / 1e3, lay.download("beauty")[..., :3])
+        lay.free()
+    assert rel_mse(out["two_level"][2], out["flat"][2]) <= 1e-3
+    with capsys.disabled():
+        print("\\nC4 two-level: %.0f MB (flat %.0f MB), build %.1f ms (flat %.1f ms), instance-tree update %.3f ms, ids identical %.6f, "
+              "16 spp frame %.1f ms = %.0f Mpaths/s (flat %.1f ms = %.0f Mpaths/s)"
+              % (info["bytes"] / 1e6, flat.accel_info()["bytes"] / 1e6, info["build_ms"], flat.accel_info()["build_ms"], upd, frac,
+                 out["two_level"][0], out["two_level"][1], out["flat"][0], out["flat"][1]))
+    two.close()
+    flat.close()

@@ -65,11 +65,14 @@ for l in dis.split("\n"):
     if m:
         sym = m.group(1)
         dm = subprocess.run(["c++filt", sym], capture_output=True, text=True).stdout.strip()
-        km = re.search(r"(k_trace_\w+)<(true|false|\(bool\)[01])>", dm) or re.search(r"(k_trace_\w+)", dm)
+        km = re.search(r"(k_trace_\w+?)<([^>]*)>", dm) or re.search(r"(k_trace_\w+)", dm)
         cur = None
         if km:
-            counting = (km.lastindex or 0) >= 2 and km.group(2) in ("true", "(bool)1")
-            name = km.group(1) + ("_count" if counting else "")
+            # template arguments: <COUNT, TWO> (stage kernels) or <TWO> (k_trace_batch, always counting)
+            targs = [a.strip() in ("true", "(bool)1") for a in km.group(2).split(",")] if (km.lastindex or 0) >= 2 else []
+            counting = len(targs) == 2 and targs[0]
+            two = targs[-1] if targs else False
+            name = km.group(1) + ("_count" if counting else "") + ("_two_level" if two else "")
             cur = result["kernels"].setdefault(name, {"total": 0, "c_node": 0, "c_tri": 0, "c_tri_double_fallback": 0})
         continue
     m = re.match(r'\s*//## File "([^"]+)", line (\d+)', l)
