@@ -20,6 +20,8 @@
 // reference loader produces from the same file.
 #include "fredholm/scene.h"
 
+#include "mesh_prep.h"
+
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -678,6 +680,41 @@ void Scene::load_obj(const std::filesystem::path& filepath)
   }
 
   // ---- geometry (scene.cpp:314-437) ----
+  // Large meshes on a machine with a CUDA device: expansion, face normals and vertex de-duplication run as
+  // kernels (mesh_prep.cu) and produce the same arrays bit for bit; FRD_GPU_MESH_PREP=0 / 1 forces the host loop
+  // / the kernels.
+  {
+    size_t total_corners = 0;
+    for (const Shape& s : shapes) total_corners += s.corners.size();
+    const char* e = getenv("FRD_GPU_MESH_PREP");
+    const bool forced_on = e && e[0] == '1', forced_off = e && e[0] == '0';
+    const bool first_model = m_vertices.empty() && m_indices.empty();  // appending to a scene keeps the host loop
+    if (!forced_off && first_model && total_corners > 0 && (forced_on || total_corners >= 300000) &&
+        frd::mesh_prep_available()) {
+      std::vector<frd::ObjCorner> corners;
+      corners.reserve(total_corners);
+      for (const Shape& s : shapes)
+        for (const ObjIndex& c : s.corners) corners.push_back(frd::ObjCorner{c.v, c.vt, c.vn});
+      frd::PreparedMesh pm;
+      try {
+        frd::prepare_mesh_gpu(pos, nrm, tex, corners, pm);
+      } catch (const std::runtime_error& err) {
+        throw std::runtime_error("failed to load " + filepath.generic_string() + ": " + err.what());
+      }
+      m_vertices = std::move(pm.vertices);
+      m_normals = std::move(pm.normals);
+      m_texcoords = std::move(pm.texcoords);
+      m_indices = std::move(pm.indices);
+      for (const Shape& s : shapes) {
+        m_submesh_offsets.push_back((unsigned int)m_material_ids.size());
+        for (int id : s.material_ids) m_material_ids.push_back((unsigned int)id);
+        m_submesh_n_faces.push_back((unsigned int)s.material_ids.size());
+        m_transforms.push_back(mat4::identity());
+      }
+      m_instance_ids.assign(m_indices.size(), 0u);  // .obj has no instancing (scene.cpp:425-427)
+      return;
+    }
+  }
   std::vector<VKey> unique;
   std::unordered_map<VKey, uint32_t, VKeyHash> lookup;
   lookup.reserve(pos.size() / 3 + 16);
@@ -733,6 +770,11 @@ void Scene::load_obj(const std::filesystem::path& filepath)
         } else {
           vid[k] = it->second;
         }
+        // quirk (scene.cpp:380-387): a vertex with a NaN component (the face normal of a degenerate triangle) equals
+        // nothing, not even itself, so the reference's `indices.push_back(unique_vertices[vertex])` inserts a fresh
+        // map entry with value 0 -- the vertex is appended, but the corner refers to vertex 0
+        for (int a = 0; a < 8; ++a)
+          if (key.v[a] != key.v[a]) vid[k] = 0;
       }
       m_indices.push_back(make_uint3(vid[0], vid[1], vid[2]));
       m_material_ids.push_back((unsigned int)s.material_ids[f]);

@@ -93,3 +93,42 @@ def test_append_without_clear(oracle_mod, tmp_path):
     o.load_scene(p, clear=False)
     assert_same(a, o.get_loaded_scene())
     assert a.n_faces == 64
+
+
+@pytest.mark.gpu
+def test_gpu_vertex_dedup_and_face_normals_equal_the_host_loop(oracle_mod, tmp_path, monkeypatch):
+    """csrc/mesh_prep.cu (expansion, face-normal generation, vertex de-duplication as kernels) against the host loop
+    of csrc/scene.cpp and the reference's loader: identical arrays, same vertex order (first occurrence), for a
+    mesh WITH normals / texcoords and for one WITHOUT (face normals, default texcoords, many duplicate corners)."""
+    import time
+    s = scenes.standard_surface_scene(96, 48, sphere_res=(24, 12))
+    for with_attributes in (True, False):
+        p = scenes.write_obj(s, str(tmp_path / ("a%d" % with_attributes)), "mesh", with_attributes=with_attributes)
+        out = {}
+        for mode in ("0", "1"):
+            monkeypatch.setenv("FRD_GPU_MESH_PREP", mode)
+            t0 = time.time()
+            sc = api.Scene()
+            sc.load_model(p)
+            out[mode] = (sc.arrays(), time.time() - t0)
+        a, b = out["0"][0], out["1"][0]
+        for k in FIELDS:
+            x, y = getattr(a, k), getattr(b, k)
+            assert x.shape == y.shape and x.tobytes() == y.tobytes(), (with_attributes, k)
+        ours, ref = load_both(oracle_mod, p)          # the reference's loader (tinyobjloader + unordered_map)
+        for k in FIELDS:                              # bytes, not ==: degenerate triangles have NaN face normals
+            assert getattr(ours, k).tobytes() == getattr(ref, k).tobytes(), (with_attributes, k)
+        print("obj with_attributes=%s: %d faces, %d unique vertices, host loop %.2f s, kernels %.2f s (incl. parse)"
+              % (with_attributes, a.n_faces, len(a.vertices), out["0"][1], out["1"][1]))
+
+
+def test_obj_degenerate_triangle_without_normals_maps_to_vertex_zero(oracle_mod, tmp_path):
+    """Reference quirk (scene.cpp:363-387): a zero-area triangle without `vn` gets a NaN face normal; a NaN vertex
+    equals nothing, so the reference appends it but `unique_vertices[vertex]` hands its corner index 0."""
+    p = tmp_path / "deg.obj"
+    p.write_text("v 0 0 0\nv 1 0 0\nv 0 1 0\nv 2 2 2\nv 3 3 3\nv 4 4 4\nf 1 2 3\nf 4 5 6\nf 1 3 2\n")
+    ours, ref = load_both(oracle_mod, str(p))
+    for k in FIELDS:
+        assert getattr(ours, k).tobytes() == getattr(ref, k).tobytes(), k
+    assert ours.indices[1].tolist() == [0, 0, 0] and np.isnan(ours.normals).any()
+    assert len(ours.vertices) == 9          # 3 + 3 NaN vertices (appended, unreferenced) + 3
