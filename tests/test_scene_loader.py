@@ -125,8 +125,9 @@ def test_gpu_vertex_dedup_and_face_normals_equal_the_host_loop(oracle_mod, tmp_p
 def test_obj_degenerate_triangle_without_normals_maps_to_vertex_zero(oracle_mod, tmp_path):
     """Reference quirk (scene.cpp:363-387): a zero-area triangle without `vn` gets a NaN face normal; a NaN vertex
     equals nothing, so the reference appends it but `unique_vertices[vertex]` hands its corner index 0."""
+    (tmp_path / "deg.mtl").write_text("newmtl m\nKd 0.5 0.5 0.5\n")
     p = tmp_path / "deg.obj"
-    p.write_text("v 0 0 0\nv 1 0 0\nv 0 1 0\nv 2 2 2\nv 3 3 3\nv 4 4 4\nf 1 2 3\nf 4 5 6\nf 1 3 2\n")
+    p.write_text("mtllib deg.mtl\no s\nv 0 0 0\nv 1 0 0\nv 0 1 0\nv 2 2 2\nv 3 3 3\nv 4 4 4\nusemtl m\nf 1 2 3\nf 4 5 6\nf 1 3 2\n")
     ours, ref = load_both(oracle_mod, str(p))
     for k in FIELDS:
         assert getattr(ours, k).tobytes() == getattr(ref, k).tobytes(), k
