@@ -246,7 +246,10 @@ def cpu_baseline(args, scene):
 
 # algorithmic HBM bytes per unit of every stage: queue entry + record in, result out
 ALGO_BYTES = {"trace_closest": 4 + 32 + 16 + 4, "trace_shadow": 48 + 16, "trace_light": 48 + 32,
-              "shade": 4 + 16 + 16 + 16 + 3 * 48 + 48 + 48 + 4, "generate": 4 * 16 + 3 * 16 + 4, "film": 16}
+              "shade": 4 + 16 + 16 + 16 + 3 * 48 + 48 + 48 + 4,
+              # beauty-only frame: radiance word zeroed (16) + origin / direction / throughput (48) + queue entry (4);
+              # the three first-hit AOV words (48 more) are only written when an AOV layer is bound
+              "generate": 16 + 3 * 16 + 4, "film": 16}
 
 
 def load_json(path):
