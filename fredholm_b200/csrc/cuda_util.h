@@ -4,6 +4,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstddef>
 #include <sstream>
 #include <stdexcept>
@@ -26,6 +27,34 @@
 
 namespace frd
 {
+
+// Grid of a persistent kernel = SMs x resident CTAs per SM of the CURRENT device, cached per device: one process
+// may drive several devices from several host threads (MultiGpuRenderer), so a plain static would be both racy and
+// wrong on a mixed box.
+class GridCache
+{
+ public:
+  int get(const void* kernel, int block)
+  {
+    int dev = 0;
+    FR_CUDA_CHECK(cudaGetDevice(&dev));
+    const bool cached = dev >= 0 && dev < kMaxDevices;
+    if (cached) {
+      const int g = m_grid[dev].load(std::memory_order_relaxed);
+      if (g) return g;
+    }
+    int sms = 0, per_sm = 0;
+    FR_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    FR_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, 0));
+    const int g = sms * (per_sm > 0 ? per_sm : 1);
+    if (cached) m_grid[dev].store(g, std::memory_order_relaxed);
+    return g;
+  }
+
+ private:
+  static constexpr int kMaxDevices = 64;
+  std::atomic<int> m_grid[kMaxDevices] = {};
+};
 
 template <typename T>
 class DevBuf

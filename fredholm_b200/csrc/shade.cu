@@ -662,14 +662,6 @@ __global__ void k_test_primary_rays(WaveParams wp, float* out)
   r[5] = d.z;
 }
 
-int persistent_grid(const void* kernel, int block)
-{
-  int dev = 0, sms = 0, per_sm = 0;
-  FR_CUDA_CHECK(cudaGetDevice(&dev));
-  FR_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  FR_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, 0));
-  return sms * (per_sm > 0 ? per_sm : 1);
-}
 
 }  // namespace
 
@@ -691,8 +683,8 @@ template <uint32_t MASK, bool TEX>
 void launch_shade_t(cudaStream_t s, const WaveParams& wp, const SceneView& sc, const WaveBuffers& wb, uint32_t depth,
                     int cls)
 {
-  static int grid = 0;
-  if (grid == 0) grid = persistent_grid(reinterpret_cast<const void*>(k_shade<MASK, TEX>), kBlock);
+  static GridCache cache;
+  const int grid = cache.get(reinterpret_cast<const void*>(k_shade<MASK, TEX>), kBlock);
   k_shade<MASK, TEX><<<grid, kBlock, 0, s>>>(wp, sc, wb, depth, cls);
   FR_CUDA_LAUNCH_CHECK();
 }
@@ -723,8 +715,8 @@ void launch_first_hit(cudaStream_t s, const WaveParams& wp, const WaveBuffers& w
 
 void launch_miss(cudaStream_t s, const WaveParams& wp, const SceneView& sc, const WaveBuffers& wb)
 {
-  static int grid = 0;
-  if (grid == 0) grid = persistent_grid(reinterpret_cast<const void*>(k_miss), kBlock);
+  static GridCache cache;
+  const int grid = cache.get(reinterpret_cast<const void*>(k_miss), kBlock);
   k_miss<<<grid, kBlock, 0, s>>>(wp, sc, wb);
   FR_CUDA_LAUNCH_CHECK();
 }

@@ -149,26 +149,21 @@ __global__ void __launch_bounds__(kBlock) k_sort_scatter(WaveBuffers wb, int whi
   }
 }
 
-int g_sort_grid = 0;
+GridCache g_sort_grid;
 
 }  // namespace
 
 void launch_coherence_sort(cudaStream_t s, const WaveBuffers& wb, const SortGrid& g, int which, uint32_t* keys,
                            uint32_t* bins, uint32_t* out)
 {
-  if (!g_sort_grid) {
-    int dev = 0, sms = 0;
-    FR_CUDA_CHECK(cudaGetDevice(&dev));
-    FR_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    g_sort_grid = sms * 8;
-  }
+  const int grid = g_sort_grid.get(reinterpret_cast<const void*>(k_sort_count), kBlock);
   const uint32_t n_bins = sort_bins(g);
   FR_CUDA_CHECK(cudaMemsetAsync(bins, 0, sizeof(uint32_t) * n_bins, s));
-  k_sort_count<<<g_sort_grid, kBlock, 0, s>>>(wb, g, which, keys, bins);
+  k_sort_count<<<grid, kBlock, 0, s>>>(wb, g, which, keys, bins);
   FR_CUDA_LAUNCH_CHECK();
   k_sort_scan<<<1, 1024, 0, s>>>(bins, n_bins);
   FR_CUDA_LAUNCH_CHECK();
-  k_sort_scatter<<<g_sort_grid, kBlock, 0, s>>>(wb, which, keys, bins, out);
+  k_sort_scatter<<<grid, kBlock, 0, s>>>(wb, which, keys, bins, out);
   FR_CUDA_LAUNCH_CHECK();
 }
 

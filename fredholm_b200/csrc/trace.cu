@@ -318,8 +318,9 @@ __global__ void __launch_bounds__(kBlock) k_trace_batch(SceneView sc, const uint
   trace_queue<false, true, TWO>(sc.bvh, pol, cursor, n, stack_column, kBlock, refill, tri_lanes);
 }
 
-int g_grid_closest = 0, g_grid_shadow = 0, g_grid_light = 0;
-int g_grid_closest2 = 0, g_grid_shadow2 = 0, g_grid_light2 = 0;  // two-level instantiations
+GridCache g_grid_closest, g_grid_shadow, g_grid_light;
+GridCache g_grid_closest2, g_grid_shadow2, g_grid_light2;  // two-level instantiations
+GridCache g_grid_batch, g_grid_batch2;
 
 // idle lanes per warp that trigger a refill (tunable for experiments: FRD_REFILL_LANES)
 int env_int(const char* name, int fallback)
@@ -351,14 +352,6 @@ int tri_lanes_any()
   return v;
 }
 
-int persistent_grid(const void* kernel, int block)
-{
-  int dev = 0, sms = 0, per_sm = 0;
-  FR_CUDA_CHECK(cudaGetDevice(&dev));
-  FR_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  FR_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, 0));
-  return sms * (per_sm > 0 ? per_sm : 1);
-}
 
 }  // namespace
 
@@ -370,16 +363,16 @@ void launch_trace_closest(cudaStream_t s, const SceneView& sc, const WaveBuffers
 {
   const int refill = depth == 0 ? refill_lanes_coherent() : refill_lanes();
   if (sc.bvh.instances) {
-    if (!g_grid_closest2) g_grid_closest2 = persistent_grid(reinterpret_cast<const void*>(k_trace_closest<false, true>), kBlock);
-    k_trace_closest<false, true><<<g_grid_closest2, kBlock, 0, s>>>(sc, wb, depth, refill, tri_lanes_closest(), order);
+    const int grid = g_grid_closest2.get(reinterpret_cast<const void*>(k_trace_closest<false, true>), kBlock);
+    k_trace_closest<false, true><<<grid, kBlock, 0, s>>>(sc, wb, depth, refill, tri_lanes_closest(), order);
     FR_CUDA_LAUNCH_CHECK();
     return;
   }
-  if (!g_grid_closest) g_grid_closest = persistent_grid(reinterpret_cast<const void*>(k_trace_closest<false, false>), kBlock);
+  const int grid = g_grid_closest.get(reinterpret_cast<const void*>(k_trace_closest<false, false>), kBlock);
   if (g_count_traversal)
-    k_trace_closest<true, false><<<g_grid_closest, kBlock, 0, s>>>(sc, wb, depth, refill, tri_lanes_closest(), order);
+    k_trace_closest<true, false><<<grid, kBlock, 0, s>>>(sc, wb, depth, refill, tri_lanes_closest(), order);
   else
-    k_trace_closest<false, false><<<g_grid_closest, kBlock, 0, s>>>(sc, wb, depth, refill, tri_lanes_closest(), order);
+    k_trace_closest<false, false><<<grid, kBlock, 0, s>>>(sc, wb, depth, refill, tri_lanes_closest(), order);
   FR_CUDA_LAUNCH_CHECK();
 }
 
@@ -388,16 +381,16 @@ void launch_trace_shadow(cudaStream_t s, const SceneView& sc, const WaveBuffers&
 {
   const int refill = coherent ? refill_lanes_coherent() : refill_lanes();
   if (sc.bvh.instances) {
-    if (!g_grid_shadow2) g_grid_shadow2 = persistent_grid(reinterpret_cast<const void*>(k_trace_shadow<false, true>), kBlock);
-    k_trace_shadow<false, true><<<g_grid_shadow2, kBlock, 0, s>>>(sc, wb, which, refill, tri_lanes_any(), order);
+    const int grid = g_grid_shadow2.get(reinterpret_cast<const void*>(k_trace_shadow<false, true>), kBlock);
+    k_trace_shadow<false, true><<<grid, kBlock, 0, s>>>(sc, wb, which, refill, tri_lanes_any(), order);
     FR_CUDA_LAUNCH_CHECK();
     return;
   }
-  if (!g_grid_shadow) g_grid_shadow = persistent_grid(reinterpret_cast<const void*>(k_trace_shadow<false, false>), kBlock);
+  const int grid = g_grid_shadow.get(reinterpret_cast<const void*>(k_trace_shadow<false, false>), kBlock);
   if (g_count_traversal)
-    k_trace_shadow<true, false><<<g_grid_shadow, kBlock, 0, s>>>(sc, wb, which, refill, tri_lanes_any(), order);
+    k_trace_shadow<true, false><<<grid, kBlock, 0, s>>>(sc, wb, which, refill, tri_lanes_any(), order);
   else
-    k_trace_shadow<false, false><<<g_grid_shadow, kBlock, 0, s>>>(sc, wb, which, refill, tri_lanes_any(), order);
+    k_trace_shadow<false, false><<<grid, kBlock, 0, s>>>(sc, wb, which, refill, tri_lanes_any(), order);
   FR_CUDA_LAUNCH_CHECK();
 }
 
@@ -408,16 +401,16 @@ void launch_trace_light(cudaStream_t s, const SceneView& sc, const WaveBuffers& 
     return;
   }
   if (sc.bvh.instances) {
-    if (!g_grid_light2) g_grid_light2 = persistent_grid(reinterpret_cast<const void*>(k_trace_light<false, true>), kBlock);
-    k_trace_light<false, true><<<g_grid_light2, kBlock, 0, s>>>(sc, wb, refill_lanes(), tri_lanes_closest(), order);
+    const int grid = g_grid_light2.get(reinterpret_cast<const void*>(k_trace_light<false, true>), kBlock);
+    k_trace_light<false, true><<<grid, kBlock, 0, s>>>(sc, wb, refill_lanes(), tri_lanes_closest(), order);
     FR_CUDA_LAUNCH_CHECK();
     return;
   }
-  if (!g_grid_light) g_grid_light = persistent_grid(reinterpret_cast<const void*>(k_trace_light<false, false>), kBlock);
+  const int grid = g_grid_light.get(reinterpret_cast<const void*>(k_trace_light<false, false>), kBlock);
   if (g_count_traversal)
-    k_trace_light<true, false><<<g_grid_light, kBlock, 0, s>>>(sc, wb, refill_lanes(), tri_lanes_closest(), order);
+    k_trace_light<true, false><<<grid, kBlock, 0, s>>>(sc, wb, refill_lanes(), tri_lanes_closest(), order);
   else
-    k_trace_light<false, false><<<g_grid_light, kBlock, 0, s>>>(sc, wb, refill_lanes(), tri_lanes_closest(), order);
+    k_trace_light<false, false><<<grid, kBlock, 0, s>>>(sc, wb, refill_lanes(), tri_lanes_closest(), order);
   FR_CUDA_LAUNCH_CHECK();
 }
 
@@ -434,12 +427,12 @@ void trace_batch_closest(const SceneView& sc, const uint32_t* d_submesh_offsets,
   d_cursor.zero();
   FR_CUDA_CHECK(cudaMemcpy(d_rays.get(), rays_host, sizeof(float) * 6ull * n, cudaMemcpyHostToDevice));
   if (sc.bvh.instances) {
-    const int grid = std::min<int>((n + kBlock - 1) / kBlock, persistent_grid(reinterpret_cast<const void*>(k_trace_batch<true>), kBlock));
+    const int grid = std::min<int>((n + kBlock - 1) / kBlock, g_grid_batch2.get(reinterpret_cast<const void*>(k_trace_batch<true>), kBlock));
     k_trace_batch<true><<<grid, kBlock>>>(sc, d_submesh_offsets, d_rays.get(), n, tmin, tmax, d_id.get(), d_tuv.get(),
                                           counters2_host ? d_cnt.get() : nullptr, d_cursor.get(), refill_lanes(),
                                           tri_lanes_closest());
   } else {
-    const int grid = std::min<int>((n + kBlock - 1) / kBlock, persistent_grid(reinterpret_cast<const void*>(k_trace_batch<false>), kBlock));
+    const int grid = std::min<int>((n + kBlock - 1) / kBlock, g_grid_batch.get(reinterpret_cast<const void*>(k_trace_batch<false>), kBlock));
     k_trace_batch<false><<<grid, kBlock>>>(sc, d_submesh_offsets, d_rays.get(), n, tmin, tmax, d_id.get(), d_tuv.get(),
                                            counters2_host ? d_cnt.get() : nullptr, d_cursor.get(), refill_lanes(),
                                            tri_lanes_closest());

@@ -31,30 +31,36 @@ r.build_accel()
 r.set_directional_light(L["sun_le"], L["sun_dir"], L["sun_angle"])
 r.load_arhosek_sky(L["turbidity"], L["albedo"])
 r.set_resolution(W, H)
-torch.cuda.set_stream(torch.cuda.ExternalStream(r.stream(), device=torch.device("cuda", local)))
-beauty = torch.zeros((H, W, 4), dtype=torch.float32, device="cuda")
-first, n = parallel.sample_slice(SPP, rank, world)
-r.set_film_mode("sum")
-r.set_sample_offset(first)
-r.render(cam, (0, 0, 0), {"beauty": beauty.data_ptr()}, min(n, 16), DEPTH)   # warm-up (allocations)
+# the data path is the C++ core's: slice render + ONE ncclReduce + scale (fr_render_sharded)
+if world > 1:
+    parallel.init_core_communicator(r, dist)
+else:
+    r.comm_init(api.comm_unique_id(), 0, 1)
+from fredholm_b200 import DeviceLayers  # noqa: E402
+lay = DeviceLayers(W, H, names=("beauty",))
+# warm-up at the REAL wave size (the default 64 Mi-path wave = 32 samples of this frame), so that no allocation
+# lands in the timed region (round 1 warmed up with 16 samples and timed a 24 GB cudaMalloc)
+lay.clear()
+r.init_render_states()
+r.render_sharded(cam, (0, 0, 0), lay, min(SPP, 64 * world), DEPTH, root=0)
 r.wait()
-beauty.zero_()
-r.set_sample_offset(first)
+lay.clear()
+r.init_render_states()
 r.reset_statistics()
 if world > 1:
     dist.barrier()
 torch.cuda.synchronize()
 t0 = time.perf_counter()
-r.render(cam, (0, 0, 0), {"beauty": beauty.data_ptr()}, n, DEPTH)
-parallel.reduce_film(dist if world > 1 else None, beauty, SPP)
-torch.cuda.synchronize()
+r.render_sharded(cam, (0, 0, 0), lay, SPP, DEPTH, root=0)
+r.wait()
+first, n = api.sample_slice(SPP, rank, world)
 secs = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
 rays = torch.tensor([float(r.statistics()["rays"])], dtype=torch.float64, device="cuda")
 if world > 1:
     dist.all_reduce(secs, op=dist.ReduceOp.MAX)
     dist.all_reduce(rays, op=dist.ReduceOp.SUM)
 if rank == 0:
-    got = beauty.cpu().numpy()
+    got = lay.download("beauty")
     out = {"config": "C3 1920x1080, %d tris, %d spp, depth %d, sample-sharded x%d, one NCCL reduce" % (s.n_faces, SPP, DEPTH, world),
            "n_gpus": world, "samples_per_gpu": n, "seconds": float(secs.item()),
            "mpaths_per_s": W * H * SPP / float(secs.item()) / 1e6, "mrays_per_s": float(rays.item()) / float(secs.item()) / 1e6,
