@@ -106,6 +106,7 @@ SIGNATURES = {
     "fr_get_sample_count": (C.c_uint32, [_vp]),
     "fr_set_film_mode": (C.c_int, [_vp, C.c_int]),
     "fr_set_max_wave_paths": (C.c_int, [_vp, C.c_uint64]),
+    "fr_set_wave_overlap": (C.c_int, [_vp, C.c_int]),
     "fr_get_wave_state_bytes": (C.c_uint64, [_vp]),
     "fr_set_single_launch": (C.c_int, [_vp, C.c_int]),
     "fr_render": (C.c_int, [_vp, _fp, C.c_float, C.c_float, C.c_float, _fp, C.POINTER(_Layers), C.c_uint32,
@@ -693,6 +694,9 @@ class Renderer:
         out = np.zeros(6, np.uint64)
         _check(lib().fr_get_traversal_counters(self._h, out.ctypes.data_as(_u64p)))
         return {k: (int(out[i]), int(out[3 + i])) for i, k in enumerate(("radiance", "shadow", "light"))}
+
+    def set_wave_overlap(self, on=True):
+        _check(lib().fr_set_wave_overlap(self._h, 1 if on else 0))
 
     def wave_state_bytes(self):
         return int(lib().fr_get_wave_state_bytes(self._h))

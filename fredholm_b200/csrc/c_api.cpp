@@ -600,6 +600,10 @@ int fr_get_statistics(fr_renderer* r, uint64_t* out6)
     out6[5] = s.rays_skipped;
   });
 }
+int fr_set_wave_overlap(fr_renderer* r, int on)
+{
+  return guarded([&] { r->renderer.set_wave_overlap(on != 0); });
+}
 uint64_t fr_get_wave_state_bytes(fr_renderer* r) { return r ? (uint64_t)r->renderer.get_wave_state_bytes() : 0; }
 int fr_set_traversal_counting(fr_renderer* r, int on)
 {

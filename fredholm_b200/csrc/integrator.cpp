@@ -23,6 +23,7 @@ Integrator::Integrator(cudaStream_t stream) : m_stream(stream)
   m_sort_mask = env_u32("FRD_SORT", 0u);
   m_sort_bits = std::min(std::max(env_u32("FRD_SORT_BITS", 4u), 1u), 7u);
   set_samples_per_warp(env_u32("FRD_SAMPLES_PER_WARP", kDefaultSamplesPerWarp));
+  m_overlap = env_u32("FRD_WAVE_OVERLAP", 0u) != 0u;
 }
 
 void Integrator::set_samples_per_warp(uint32_t spw)
@@ -39,7 +40,8 @@ void Integrator::set_coherence_sort(uint32_t queue_mask, uint32_t cell_bits)
 }
 
 // sorts queue `which` and returns the order to trace it in (nullptr: sort disabled for it)
-const uint32_t* Integrator::sorted(const SceneView& scene, const WaveBuffers& wb, int which, bool use_octant)
+const uint32_t* Integrator::sorted(cudaStream_t s, WaveSet& set, const SceneView& scene, const WaveBuffers& wb, int which,
+                                   bool use_octant)
 {
   SortGrid g;
   g.lo = scene.bounds_lo;
@@ -50,10 +52,10 @@ const uint32_t* Integrator::sorted(const SceneView& scene, const WaveBuffers& wb
   g.inv_cell = make_float3(cells / ex, cells / ey, cells / ez);
   g.cell_bits = m_sort_bits;
   g.use_octant = use_octant ? 1u : 0u;
-  m_sort_bins.reserve(size_t(1) << (3 * m_sort_bits + 3));
-  launch_coherence_sort(m_stream, wb, g, which, m_sort_keys.get(), m_sort_bins.get(), m_sort_out.get());
+  set.sort_bins.reserve(size_t(1) << (3 * m_sort_bits + 3));
+  launch_coherence_sort(s, wb, g, which, set.sort_keys.get(), set.sort_bins.get(), set.sort_out.get());
   m_launches += 2;  // three kernels, one of them counted by stage()
-  return m_sort_out.get();
+  return set.sort_out.get();
 }
 
 Integrator::~Integrator()
@@ -63,6 +65,13 @@ Integrator::~Integrator()
     cudaEventDestroy(t.e1);
   }
   for (auto e : m_event_pool) cudaEventDestroy(e);
+  if (m_ev_start) cudaEventDestroy(m_ev_start);
+  for (auto e : m_ev_film)
+    if (e) cudaEventDestroy(e);
+  if (m_aux_stream) {
+    cudaStreamSynchronize(m_aux_stream);
+    cudaStreamDestroy(m_aux_stream);
+  }
 }
 
 cudaEvent_t Integrator::get_event()
@@ -84,25 +93,31 @@ const char* const kStageNames[STAGE_COUNT] = {"generate", "trace_closest", "shad
 }
 
 template <typename F>
-void Integrator::stage(int id, F&& launch)
+void Integrator::stage(cudaStream_t s, int id, F&& launch)
 {
   FR_NVTX_RANGE(kStageNames[id]);
   if (!m_time_stages) {
     launch();
   } else {
     TimedLaunch t{id, get_event(), get_event()};
-    FR_CUDA_CHECK(cudaEventRecord(t.e0, m_stream));
+    FR_CUDA_CHECK(cudaEventRecord(t.e0, s));
     launch();
-    FR_CUDA_CHECK(cudaEventRecord(t.e1, m_stream));
+    FR_CUDA_CHECK(cudaEventRecord(t.e1, s));
     m_timed.push_back(t);
   }
   m_launches++;
 }
 
+void Integrator::sync_all_streams()
+{
+  FR_CUDA_CHECK(cudaStreamSynchronize(m_stream));
+  if (m_aux_stream) FR_CUDA_CHECK(cudaStreamSynchronize(m_aux_stream));
+}
+
 StageTimes Integrator::stage_times()
 {
   StageTimes out;
-  FR_CUDA_CHECK(cudaStreamSynchronize(m_stream));
+  sync_all_streams();
   for (auto& t : m_timed) {
     float ms = 0.0f;
     FR_CUDA_CHECK(cudaEventElapsedTime(&ms, t.e0, t.e1));
@@ -115,91 +130,167 @@ StageTimes Integrator::stage_times()
   return out;
 }
 
-void Integrator::ensure_capacity(size_t n_slots)
+// ---- wave sets -------------------------------------------------------------------------------------------
+void Integrator::WaveSet::grow_core(size_t n_slots)
 {
-  if (m_ctl.size() == 0) {
-    m_ctl.alloc(1);
-    m_ctl.zero(m_stream);
-  }
-  if (n_slots <= m_capacity) return;
-  // buffers are in use by work already queued on the stream
-  FR_CUDA_CHECK(cudaStreamSynchronize(m_stream));
-  // Not valid until every buffer below has its new size: if one allocation throws (a 64 Mi-path wave is ~25 GB),
-  // the capacity stays 0 and all wave buffers are released, so a later render() with a smaller wave reallocates
-  // everything instead of launching on a half-grown set.
-  m_capacity = 0;
-  try {
-    grow_wave_buffers(n_slots);
-  } catch (...) {
-    release_wave_buffers();
-    throw;
-  }
-  m_capacity = n_slots;
+  ray_o.alloc(n_slots);
+  ray_d.alloc(n_slots);
+  hit.alloc(n_slots);
+  thr.alloc(n_slots);
+  L.alloc(n_slots);
+  queue[0].alloc(n_slots);
+  queue[1].alloc(n_slots);
+  shadow[1].alloc(n_slots);
+  for (auto& q : class_queue) q.alloc(n_slots);
+  light.alloc(n_slots);
+  // the optional buffers follow on demand; what exists is dropped so that it regrows to the new size
+  aov0.release();
+  aov1.release();
+  aov2.release();
+  shadow[0].release();
+  shadow[2].release();
+  sort_keys.release();
+  sort_out.release();
 }
 
-// Buffers only some renders need -- the first-hit AOV words (48 B / path), the sun and area-light NEE queues
-// (48 B / path each), the coherence-sort scratch (8 B / path) -- are allocated when a render first needs them, at
-// the capacity of the core set: a beauty-only render of a scene without emitters keeps 268 B / path instead of 372.
-void Integrator::ensure_optional(const WaveNeeds& need)
+void Integrator::WaveSet::release()
 {
+  ray_o.release();
+  ray_d.release();
+  hit.release();
+  thr.release();
+  L.release();
+  aov0.release();
+  aov1.release();
+  aov2.release();
+  queue[0].release();
+  queue[1].release();
+  for (auto& s : shadow) s.release();
+  for (auto& q : class_queue) q.release();
+  light.release();
+  sort_keys.release();
+  sort_out.release();
+  capacity = 0;
+}
+
+size_t Integrator::WaveSet::bytes() const
+{
+  size_t b = ray_o.bytes() + ray_d.bytes() + hit.bytes() + thr.bytes() + L.bytes() + aov0.bytes() + aov1.bytes() + aov2.bytes() +
+             queue[0].bytes() + queue[1].bytes() + light.bytes() + sort_keys.bytes() + sort_out.bytes();
+  for (const auto& s : shadow) b += s.bytes();
+  for (const auto& q : class_queue) b += q.bytes();
+  return b;
+}
+
+WaveBuffers Integrator::WaveSet::view() const
+{
+  WaveBuffers wb;
+  wb.ray_o = ray_o.get();
+  wb.ray_d = ray_d.get();
+  wb.hit = hit.get();
+  wb.thr = thr.get();
+  wb.L = L.get();
+  wb.aov0 = aov0.get();
+  wb.aov1 = aov1.get();
+  wb.aov2 = aov2.get();
+  wb.queue[0] = queue[0].get();
+  wb.queue[1] = queue[1].get();
+  for (int k = 0; k < 3; ++k) wb.shadow[k] = shadow[k].get();
+  for (int c = 0; c < CLS_COUNT; ++c) wb.class_queue[c] = class_queue[c].get();
+  wb.light = light.get();
+  wb.ctl = ctl.get();
+  wb.first_hit = nullptr;
+  wb.pix_aov0 = wb.pix_aov1 = wb.pix_aov2 = nullptr;
+  return wb;
+}
+
+// Core buffers for n_slots paths plus the optional ones this render needs -- the first-hit AOV words (48 B / path),
+// the sun and area-light NEE queues (48 B / path each), the coherence-sort scratch (8 B / path): a beauty-only
+// render of a scene without emitters keeps 268 B / path instead of 372.
+void Integrator::ensure_capacity(WaveSet& set, size_t n_slots, const WaveNeeds& need)
+{
+  if (set.ctl.size() == 0) {
+    set.ctl.alloc(1);
+    set.ctl.zero(m_stream);
+  }
   bool synced = false;
-  auto grow = [&](auto& buf, bool wanted) {
-    if (!wanted || buf.size() >= m_capacity) return;
-    if (!synced) FR_CUDA_CHECK(cudaStreamSynchronize(m_stream));
+  auto sync_once = [&] {
+    // the buffers are in use by work already queued
+    if (!synced) sync_all_streams();
     synced = true;
-    buf.alloc(m_capacity);
   };
-  grow(m_aov0, need.aov);
-  grow(m_aov1, need.aov);
-  grow(m_aov2, need.aov);
-  grow(m_shadow[0], need.sun_queue);
-  grow(m_shadow[2], need.area_queue);
-  grow(m_sort_keys, need.sort);
-  grow(m_sort_out, need.sort);
-  m_state_bytes = m_capacity * kWaveBytesCore + m_aov0.bytes() + m_aov1.bytes() + m_aov2.bytes() + m_shadow[0].bytes() +
-                  m_shadow[2].bytes() + m_sort_keys.bytes() + m_sort_out.bytes();
+  if (n_slots > set.capacity) {
+    sync_once();
+    // Not valid until every buffer has its new size: if one allocation throws (a 64 Mi-path wave is tens of GB),
+    // the capacity stays 0 and the set is released, so a later render() with a smaller wave reallocates
+    // everything instead of launching on a half-grown set.
+    set.capacity = 0;
+    try {
+      set.grow_core(n_slots);
+    } catch (...) {
+      set.release();
+      throw;
+    }
+    set.capacity = n_slots;
+  }
+  auto grow = [&](auto& buf, bool wanted) {
+    if (!wanted || buf.size() >= set.capacity) return;
+    sync_once();
+    buf.alloc(set.capacity);
+  };
+  grow(set.aov0, need.aov);
+  grow(set.aov1, need.aov);
+  grow(set.aov2, need.aov);
+  grow(set.shadow[0], need.sun_queue);
+  grow(set.shadow[2], need.area_queue);
+  grow(set.sort_keys, need.sort);
+  grow(set.sort_out, need.sort);
+  m_state_bytes = m_set[0].bytes() + m_set[1].bytes();
 }
 
-void Integrator::release_wave_buffers()
+// one wave: camera rays, max_depth bounces of { closest hit, shade per material class, visibility rays, MIS rays }
+// (everything up to, not including, the film)
+void Integrator::render_wave(cudaStream_t s, WaveSet& set, const WaveBuffers& wb, const WaveParams& wp, const SceneView& scene,
+                             uint32_t class_mask)
 {
-  m_ray_o.release();
-  m_ray_d.release();
-  m_hit.release();
-  m_thr.release();
-  m_L.release();
-  m_aov0.release();
-  m_aov1.release();
-  m_aov2.release();
-  m_queue[0].release();
-  m_queue[1].release();
-  for (auto& s : m_shadow) s.release();
-  for (auto& q : m_class_queue) q.release();
-  m_light.release();
-  m_sort_keys.release();
-  m_sort_out.release();
-  m_state_bytes = 0;
-}
-
-void Integrator::grow_wave_buffers(size_t n_slots)
-{
-  m_ray_o.alloc(n_slots);
-  m_ray_d.alloc(n_slots);
-  m_hit.alloc(n_slots);
-  m_thr.alloc(n_slots);
-  m_L.alloc(n_slots);
-  m_queue[0].alloc(n_slots);
-  m_queue[1].alloc(n_slots);
-  m_shadow[1].alloc(n_slots);
-  for (auto& q : m_class_queue) q.alloc(n_slots);
-  m_light.alloc(n_slots);
-  // the optional sets follow on demand (ensure_optional); what exists is dropped so that it regrows to the new size
-  m_aov0.release();
-  m_aov1.release();
-  m_aov2.release();
-  m_shadow[0].release();
-  m_shadow[2].release();
-  m_sort_keys.release();
-  m_sort_out.release();
+  FR_NVTX_RANGE("wave");
+  stage(s, STAGE_ADVANCE, [&] {
+    launch_wave_begin(s, wb, (unsigned long long)wp.n_samples * wp.film.width * wp.film.height);
+  });
+  stage(s, STAGE_GENERATE, [&] { launch_generate(s, wp, wb); });
+  for (uint32_t depth = 0; depth < wp.max_depth; ++depth) {
+#if FR_HAVE_NVTX
+    char bounce_name[24];
+    snprintf(bounce_name, sizeof(bounce_name), "bounce %u", depth);
+    FR_NVTX_RANGE(bounce_name);
+#endif
+    // coherence sort (queue management, booked under "advance"): each queue is sorted right
+    // before it is traced, so one scratch order buffer serves all of them
+    const uint32_t* order = nullptr;
+    auto sort_queue = [&](uint32_t bit, int which, bool use_octant) {
+      order = nullptr;
+      if (m_sort_mask & bit) stage(s, STAGE_ADVANCE, [&] { order = sorted(s, set, scene, wb, which, use_octant); });
+    };
+    if (depth > 0) sort_queue(1u, SORT_RADIANCE0 + (int)(depth & 1u), true);
+    stage(s, STAGE_TRACE_CLOSEST, [&] { launch_trace_closest(s, scene, wb, depth, order); });
+    if (depth == 0 && m_single_launch) stage(s, STAGE_SHADE, [&] { launch_first_hit(s, wp, wb); });
+    if (depth == 0) stage(s, STAGE_SHADE, [&] { launch_miss(s, wp, scene, wb); });
+    for (int c = 0; c < CLS_MISS; ++c)
+      if (class_mask & (1u << c)) stage(s, STAGE_SHADE, [&] { launch_shade(s, wp, scene, wb, depth, c); });
+    if (scene.has_dir_light) {
+      sort_queue(2u, SORT_SHADOW0, false);  // all sun rays point the same way
+      stage(s, STAGE_TRACE_SHADOW, [&] { launch_trace_shadow(s, scene, wb, 0, order, depth == 0); });
+    }
+    sort_queue(4u, SORT_SHADOW1, true);
+    stage(s, STAGE_TRACE_SHADOW, [&] { launch_trace_shadow(s, scene, wb, 1, order); });
+    if (scene.n_lights > 0) {
+      sort_queue(8u, SORT_SHADOW2, true);
+      stage(s, STAGE_TRACE_SHADOW, [&] { launch_trace_shadow(s, scene, wb, 2, order); });
+    }
+    sort_queue(16u, SORT_LIGHT, true);
+    stage(s, STAGE_TRACE_LIGHT, [&] { launch_trace_light(s, scene, wb, order); });
+    stage(s, STAGE_ADVANCE, [&] { launch_advance(s, wb); });
+  }
 }
 
 void Integrator::render(const SceneView& scene, const fredholm::CameraParams& camera, uint32_t width,
@@ -216,37 +307,30 @@ void Integrator::render(const SceneView& scene, const fredholm::CameraParams& ca
   need.sun_queue = scene.has_dir_light != 0;
   need.area_queue = scene.n_lights > 0;
   need.sort = m_sort_mask != 0;
-  // a wave = whole sample groups (spw samples of every pixel), at least one
-  size_t groups_per_wave = std::max<size_t>(
-      1, std::min<size_t>(film_groups(film, n_samples), m_max_wave_paths / film.slots_per_group));
-  if (groups_per_wave * film.slots_per_group > m_capacity) {
-    // growing: never ask for more than the device can give (90 % of what is free plus what the wave holds now)
+  // paths in flight = whole sample groups (spw samples of every pixel), at least one
+  const size_t groups_total = film_groups(film, n_samples);
+  size_t groups_in_flight = std::max<size_t>(1, std::min<size_t>(groups_total, m_max_wave_paths / film.slots_per_group));
+  if (groups_in_flight * film.slots_per_group > m_set[0].capacity + m_set[1].capacity) {
+    // growing: never ask for more than the device can give (90 % of what is free plus what the waves hold now)
     size_t free_b = 0, total_b = 0;
     FR_CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
     const size_t fit = (size_t)(0.9 * (double)(free_b + m_state_bytes)) / (wave_bytes_per_slot(need) * film.slots_per_group);
-    groups_per_wave = std::max<size_t>(1, std::min(groups_per_wave, fit));
+    groups_in_flight = std::max<size_t>(1, std::min(groups_in_flight, fit));
   }
+  // two waves in flight when asked for and when the render has at least two waves' worth of samples
+  const bool overlap = m_overlap && !m_time_stages && !m_single_launch && groups_in_flight >= 2 && groups_total >= 2;
+  const size_t groups_per_wave = overlap ? groups_in_flight / 2 : groups_in_flight;
   const uint32_t per_wave = (uint32_t)(groups_per_wave << spw_log2);
-  ensure_capacity(groups_per_wave * film.slots_per_group);
-  ensure_optional(need);
+  const int n_sets = overlap && groups_total > groups_per_wave ? 2 : 1;
+  for (int k = 0; k < n_sets; ++k) ensure_capacity(m_set[k], groups_per_wave * film.slots_per_group, need);
+  if (n_sets == 1 && m_set[1].capacity && !m_overlap) {
+    // overlap was switched off: give the second set back
+    sync_all_streams();
+    m_set[1].release();
+    m_state_bytes = m_set[0].bytes();
+  }
 
-  WaveBuffers wb;
-  wb.ray_o = m_ray_o.get();
-  wb.ray_d = m_ray_d.get();
-  wb.hit = m_hit.get();
-  wb.thr = m_thr.get();
-  wb.L = m_L.get();
-  wb.aov0 = m_aov0.get();
-  wb.aov1 = m_aov1.get();
-  wb.aov2 = m_aov2.get();
-  wb.queue[0] = m_queue[0].get();
-  wb.queue[1] = m_queue[1].get();
-  for (int k = 0; k < 3; ++k) wb.shadow[k] = m_shadow[k].get();
-  for (int c = 0; c < CLS_COUNT; ++c) wb.class_queue[c] = m_class_queue[c].get();
-  wb.light = m_light.get();
-  wb.ctl = m_ctl.get();
-  wb.first_hit = nullptr;
-  wb.pix_aov0 = wb.pix_aov1 = wb.pix_aov2 = nullptr;
+  WaveBuffers wb[2] = {m_set[0].view(), m_set[1].view()};
   if (m_single_launch) {
     const size_t n_pixels = (size_t)width * height;
     m_first_hit.reserve(n_pixels);
@@ -255,15 +339,30 @@ void Integrator::render(const SceneView& scene, const fredholm::CameraParams& ca
       m_pix_aov[k].reserve(n_pixels);
       FR_CUDA_CHECK(cudaMemsetAsync(m_pix_aov[k].get(), 0, n_pixels * sizeof(float4), m_stream));
     }
-    wb.first_hit = m_first_hit.get();
-    wb.pix_aov0 = m_pix_aov[0].get();
-    wb.pix_aov1 = m_pix_aov[1].get();
-    wb.pix_aov2 = m_pix_aov[2].get();
+    wb[0].first_hit = m_first_hit.get();
+    wb[0].pix_aov0 = m_pix_aov[0].get();
+    wb[0].pix_aov1 = m_pix_aov[1].get();
+    wb[0].pix_aov2 = m_pix_aov[2].get();
+  }
+
+  cudaStream_t streams[2] = {m_stream, m_stream};
+  if (n_sets == 2) {
+    if (!m_aux_stream) {
+      FR_CUDA_CHECK(cudaStreamCreateWithFlags(&m_aux_stream, cudaStreamNonBlocking));
+      FR_CUDA_CHECK(cudaEventCreateWithFlags(&m_ev_start, cudaEventDisableTiming));
+      for (auto& e : m_ev_film) FR_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    streams[1] = m_aux_stream;
+    // the second stream starts after whatever the caller queued on the renderer's stream (layer clears)
+    FR_CUDA_CHECK(cudaEventRecord(m_ev_start, m_stream));
+    FR_CUDA_CHECK(cudaStreamWaitEvent(m_aux_stream, m_ev_start, 0));
   }
 
   FR_NVTX_RANGE("render");
-  for (uint32_t done = 0; done < n_samples; done += per_wave) {
-    FR_NVTX_RANGE("wave");
+  uint32_t wave = 0;
+  for (uint32_t done = 0; done < n_samples; done += per_wave, ++wave) {
+    const int k = n_sets == 2 ? (int)(wave & 1u) : 0;
+    cudaStream_t s = streams[k];
     WaveParams wp;
     wp.film = film;
     wp.n_samples = std::min(per_wave, n_samples - done);
@@ -273,44 +372,14 @@ void Integrator::render(const SceneView& scene, const fredholm::CameraParams& ca
     wp.want_aov = (layers.position || layers.normal || layers.depth || layers.texcoord || layers.albedo) ? 1u : 0u;
     wp.single_launch = m_single_launch ? 1u : 0u;
     wp.camera = camera;
-
-    stage(STAGE_ADVANCE, [&] { launch_wave_begin(m_stream, wb, (unsigned long long)wp.n_samples * width * height); });
-    stage(STAGE_GENERATE, [&] { launch_generate(m_stream, wp, wb); });
-    for (uint32_t depth = 0; depth < max_depth; ++depth) {
-#if FR_HAVE_NVTX
-      char bounce_name[24];
-      snprintf(bounce_name, sizeof(bounce_name), "bounce %u", depth);
-      FR_NVTX_RANGE(bounce_name);
-#endif
-      // coherence sort (queue management, booked under "advance"): each queue is sorted right
-      // before it is traced, so one scratch order buffer serves all of them
-      const uint32_t* order = nullptr;
-      auto sort_queue = [&](uint32_t bit, int which, bool use_octant) {
-        order = nullptr;
-        if (m_sort_mask & bit) stage(STAGE_ADVANCE, [&] { order = sorted(scene, wb, which, use_octant); });
-      };
-      if (depth > 0) sort_queue(1u, SORT_RADIANCE0 + (int)(depth & 1u), true);
-      stage(STAGE_TRACE_CLOSEST, [&] { launch_trace_closest(m_stream, scene, wb, depth, order); });
-      if (depth == 0 && m_single_launch) stage(STAGE_SHADE, [&] { launch_first_hit(m_stream, wp, wb); });
-      if (depth == 0) stage(STAGE_SHADE, [&] { launch_miss(m_stream, wp, scene, wb); });
-      for (int c = 0; c < CLS_MISS; ++c)
-        if (class_mask & (1u << c)) stage(STAGE_SHADE, [&] { launch_shade(m_stream, wp, scene, wb, depth, c); });
-      if (scene.has_dir_light) {
-        sort_queue(2u, SORT_SHADOW0, false);  // all sun rays point the same way
-        stage(STAGE_TRACE_SHADOW, [&] { launch_trace_shadow(m_stream, scene, wb, 0, order, depth == 0); });
-      }
-      sort_queue(4u, SORT_SHADOW1, true);
-      stage(STAGE_TRACE_SHADOW, [&] { launch_trace_shadow(m_stream, scene, wb, 1, order); });
-      if (scene.n_lights > 0) {
-        sort_queue(8u, SORT_SHADOW2, true);
-        stage(STAGE_TRACE_SHADOW, [&] { launch_trace_shadow(m_stream, scene, wb, 2, order); });
-      }
-      sort_queue(16u, SORT_LIGHT, true);
-      stage(STAGE_TRACE_LIGHT, [&] { launch_trace_light(m_stream, scene, wb, order); });
-      stage(STAGE_ADVANCE, [&] { launch_advance(m_stream, wb); });
-    }
-    stage(STAGE_FILM, [&] { launch_film(m_stream, wp, wb, layers, film_mode); });
+    render_wave(s, m_set[k], wb[k], wp, scene, class_mask);
+    // the film applies the waves in sample order (streaming mean): wave w's film runs after wave w-1's
+    if (n_sets == 2 && wave > 0) FR_CUDA_CHECK(cudaStreamWaitEvent(s, m_ev_film[(wave - 1) & 1u], 0));
+    stage(s, STAGE_FILM, [&] { launch_film(s, wp, wb[k], layers, film_mode); });
+    if (n_sets == 2) FR_CUDA_CHECK(cudaEventRecord(m_ev_film[wave & 1u], s));
   }
+  // whatever follows on the renderer's stream (read-back, post-process) sees the finished layers
+  if (n_sets == 2 && wave > 0 && ((wave - 1) & 1u) == 1u) FR_CUDA_CHECK(cudaStreamWaitEvent(m_stream, m_ev_film[1], 0));
 }
 
 void Integrator::scale_layers(const fredholm::RenderLayer& layers, uint32_t n_pixels, float scale)
@@ -323,18 +392,20 @@ RenderStats Integrator::stats()
 {
   RenderStats s;
   s.launches = m_launches;
-  if (m_ctl.size() == 0) return s;
-  WaveControl h;
-  FR_CUDA_CHECK(cudaStreamSynchronize(m_stream));
-  FR_CUDA_CHECK(cudaMemcpy(&h, m_ctl.get(), sizeof(h), cudaMemcpyDeviceToHost));
-  s.paths = h.paths;
-  s.rays_closest = h.rays_closest;
-  s.rays_shadow = h.rays_shadow;
-  s.rays_light = h.rays_light;
-  s.rays_skipped = h.rays_skipped;
-  for (int i = 0; i < 3; ++i) {
-    s.nodes[i] = h.nodes[i];
-    s.tris[i] = h.tris[i];
+  sync_all_streams();
+  for (const WaveSet& set : m_set) {
+    if (set.ctl.size() == 0) continue;
+    WaveControl h;
+    FR_CUDA_CHECK(cudaMemcpy(&h, set.ctl.get(), sizeof(h), cudaMemcpyDeviceToHost));
+    s.paths += h.paths;
+    s.rays_closest += h.rays_closest;
+    s.rays_shadow += h.rays_shadow;
+    s.rays_light += h.rays_light;
+    s.rays_skipped += h.rays_skipped;
+    for (int i = 0; i < 3; ++i) {
+      s.nodes[i] += h.nodes[i];
+      s.tris[i] += h.tris[i];
+    }
   }
   return s;
 }
@@ -342,10 +413,10 @@ RenderStats Integrator::stats()
 void Integrator::reset_stats()
 {
   m_launches = 0;
-  if (m_ctl.size()) {
-    FR_CUDA_CHECK(cudaStreamSynchronize(m_stream));
-    m_ctl.zero(m_stream);
-  }
+  sync_all_streams();
+  for (WaveSet& set : m_set)
+    if (set.ctl.size()) set.ctl.zero(m_stream);
+  FR_CUDA_CHECK(cudaStreamSynchronize(m_stream));
 }
 
 }  // namespace frd

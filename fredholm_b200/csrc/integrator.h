@@ -78,6 +78,12 @@ class Integrator
   void set_coherence_sort(uint32_t queue_mask, uint32_t cell_bits);
   uint32_t coherence_sort_mask() const { return m_sort_mask; }
 
+  // Two waves in flight on two streams (off by default): `max_wave_paths` is then split between them.  Sample
+  // values and the order in which the film applies them do not change.  Ignored while stage timing is on (the
+  // per-stage times would include the other stream's kernels) and in single-launch mode.
+  void set_wave_overlap(bool on) { m_overlap = on; }
+  bool wave_overlap() const { return m_overlap; }
+
   // per-stage device time (CUDA events around every launch, on the launching stream)
   void set_stage_timing(bool on) { m_time_stages = on; }
   StageTimes stage_times();  // synchronises, returns and clears the accumulated times
@@ -97,14 +103,33 @@ class Integrator
     return kWaveBytesCore + (n.aov ? 3 * sizeof(float4) : 0) + (n.sun_queue ? sizeof(ShadowRay) : 0) +
            (n.area_queue ? sizeof(ShadowRay) : 0) + (n.sort ? 2 * sizeof(uint32_t) : 0);
   }
-  void ensure_capacity(size_t n_slots);
-  void ensure_optional(const WaveNeeds& need);
-  void grow_wave_buffers(size_t n_slots);
-  void release_wave_buffers();
+
+  // Everything one wave in flight owns: path state, queues, control block, sort scratch.  The integrator keeps
+  // two of them so that (set_wave_overlap) consecutive waves of a render can run on two streams, the late,
+  // nearly empty bounces of one under the full launches of the next.
+  struct WaveSet {
+    DevBuf<float4> ray_o, ray_d, hit, thr, L, aov0, aov1, aov2;
+    DevBuf<uint32_t> queue[2];
+    DevBuf<uint32_t> class_queue[CLS_COUNT];
+    DevBuf<ShadowRay> shadow[3];
+    DevBuf<LightRay> light;
+    DevBuf<WaveControl> ctl;
+    DevBuf<uint32_t> sort_keys, sort_out, sort_bins;
+    size_t capacity = 0;  // path slots of the core set; 0 while the set is not valid
+
+    void grow_core(size_t n_slots);
+    void release();
+    size_t bytes() const;
+    WaveBuffers view() const;
+  };
+  void ensure_capacity(WaveSet& set, size_t n_slots, const WaveNeeds& need);
+  void sync_all_streams();
 
   cudaStream_t m_stream;
-  size_t m_max_wave_paths = size_t(1) << 26;  // 64 Mi paths (24 GB of wave state)
-  size_t m_capacity = 0;
+  cudaStream_t m_aux_stream = nullptr;            // second wave in flight (created on first use)
+  cudaEvent_t m_ev_start = nullptr, m_ev_film[2] = {nullptr, nullptr};
+  bool m_overlap = false;
+  size_t m_max_wave_paths = size_t(1) << 26;  // 64 Mi paths in flight (17.6 GB of wave state for a beauty-only frame)
   uint32_t m_spw_log2 = 0;
   size_t m_state_bytes = 0;
   unsigned long long m_launches = 0;
@@ -118,21 +143,17 @@ class Integrator
   std::vector<cudaEvent_t> m_event_pool;
   cudaEvent_t get_event();
   template <typename F>
-  void stage(int id, F&& launch);
+  void stage(cudaStream_t s, int id, F&& launch);
 
-  DevBuf<float4> m_ray_o, m_ray_d, m_hit, m_thr, m_L, m_aov0, m_aov1, m_aov2;
+  WaveSet m_set[2];
   bool m_single_launch = false;
   DevBuf<uint32_t> m_first_hit;           // [n_pixels], single-launch mode only
   DevBuf<float4> m_pix_aov[3];            // [n_pixels] each
-  DevBuf<uint32_t> m_queue[2];
-  DevBuf<uint32_t> m_class_queue[CLS_COUNT];
-  DevBuf<ShadowRay> m_shadow[3];
-  DevBuf<LightRay> m_light;
-  DevBuf<WaveControl> m_ctl;
 
   uint32_t m_sort_mask, m_sort_bits;
-  DevBuf<uint32_t> m_sort_keys, m_sort_out, m_sort_bins;
-  const uint32_t* sorted(const SceneView& scene, const WaveBuffers& wb, int which, bool use_octant);
+  const uint32_t* sorted(cudaStream_t s, WaveSet& set, const SceneView& scene, const WaveBuffers& wb, int which, bool use_octant);
+  void render_wave(cudaStream_t s, WaveSet& set, const WaveBuffers& wb, const WaveParams& wp, const SceneView& scene,
+                   uint32_t class_mask);
 };
 
 }  // namespace frd

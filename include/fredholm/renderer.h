@@ -130,6 +130,9 @@ class Renderer
   void scale_layers(const RenderLayer& render_layer, float scale);
   void set_max_wave_paths(size_t n_paths);
   size_t get_wave_state_bytes() const;  // device memory the integrator holds for path state and ray queues
+  // two waves in flight on two CUDA streams (max_wave_paths is split between them): the late, nearly empty
+  // bounces of one wave run under the full launches of the next.  Sample values and film order are unchanged.
+  void set_wave_overlap(bool on);
   // One render(n_samples) call behaves like ONE reference launch of n_samples: payload.firsthit and the
   // first-hit AOVs outlive the sample loop (pt.cu:432-433, 744-759) -- what app/rtcamp8.cpp produces.  Off by
   // default: render(n_samples) equals n_samples launches of one sample, what the reference GUI produces.

@@ -101,6 +101,19 @@ def test_deterministic_and_wave_independent(big):
     assert np.isfinite(a).all() and a[..., :3].mean() > 0.1
 
 
+def test_two_waves_in_flight_give_the_same_image(big):
+    """set_wave_overlap: consecutive waves on two streams, film order kept by events -- bit-identical image."""
+    _, r, cam = big
+    a = render(r, cam, 8, wave=1 << 22)["beauty"]            # four waves of two samples, one after the other
+    r.set_wave_overlap(True)
+    b = render(r, cam, 8, wave=1 << 23)["beauty"]            # the same four waves, two in flight
+    st = r.statistics()
+    r.set_wave_overlap(False)
+    c = render(r, cam, 8)["beauty"]
+    assert np.array_equal(a, b) and np.array_equal(a, c)
+    assert st["paths"] > 0
+
+
 def test_sample_slices_sum_to_whole(big):
     """Multi-GPU decomposition on one GPU: slices rendered in SUM mode at their sample offset,
     added and divided, equal the single render (fp32 summation order only)."""

@@ -8,8 +8,11 @@ L = scenes.STANDARD_LIGHTING; C = scenes.STANDARD_CAMERA
 cam = Camera(api.camera_walk(C["origin"], 0.0, 150.0, 0, 0.0), C["fov"], C["F"], C["focus"])
 W, H, SPP, DEPTH = 1920, 1080, 64, 10
 slots = ((W + 7) // 8) * ((H + 3) // 4) * 32
-for wave_spp in (4, 8, 16, 32, 64):
-    r = Renderer(0); r.set_scene(s); r.build_accel()
+import numpy as np
+ref_img = None
+for wave_spp, overlap in ((64, 0), (32, 0), (16, 0), (8, 0), (4, 0), (64, 1), (32, 1), (16, 1), (8, 1)):
+    # with overlap the paths in flight are split over two waves on two streams: "in flight" = wave_spp samples
+    r = Renderer(0); r.set_scene(s); r.build_accel(); r.set_wave_overlap(bool(overlap))
     r.set_directional_light(L["sun_le"], L["sun_dir"], L["sun_angle"]); r.load_arhosek_sky(L["turbidity"], L["albedo"])
     r.set_resolution(W, H); r.set_max_wave_paths(slots * wave_spp)
     lay = DeviceLayers(W, H, names=("beauty",))
@@ -22,6 +25,9 @@ for wave_spp in (4, 8, 16, 32, 64):
     e1 = r.record_event(); r.wait()
     ms = api.event_elapsed_ms(e0, e1) / 3
     st = r.statistics()
-    print(json.dumps(dict(samples_per_wave=wave_spp, waves_per_frame=SPP // wave_spp, wave_state_gb=round(r.wave_state_bytes() / 1e9, 2),
+    img = lay.download("beauty")
+    if ref_img is None:
+        ref_img = img
+    print(json.dumps(dict(samples_in_flight=wave_spp, overlap=overlap, identical_image=bool(np.array_equal(img, ref_img)), wave_state_gb=round(r.wave_state_bytes() / 1e9, 2),
                           frame_ms=round(ms, 2), mpaths_per_s=round(st["paths"] / 3 / ms / 1e3, 1), launches_per_frame=st["kernel_launches"] // 3)), flush=True)
     lay.free(); r.close()
