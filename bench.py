@@ -192,18 +192,21 @@ def run_reference(args):
     tiles = reference_tiles(args.width, args.height)
     for _ in range(args.warmup):
         _reference_pass(o, cam, args, tiles, max(1, args.spp // 16), cores)   # short: the CPU has no clocks to ramp
+    # a step is the tiles at all 64 samples (~8 s on 16 cores); a long run (the driver's --steps 25) takes the first
+    # 16 samples of every sampled pixel per step instead -- one whole CMJ pattern -- so that it still ends in minutes
+    ref_spp = args.spp if args.steps <= 8 else max(16, args.spp // 4)
     t = 0.0
     n_paths = rays = 0
     for _ in range(args.steps):
-        secs, n, rc = _reference_pass(o, cam, args, tiles, args.spp, cores)
+        secs, n, rc = _reference_pass(o, cam, args, tiles, ref_spp, cores)
         t += secs
         n_paths += n
         rays += rc["rays"]
     value = n_paths / t / 1e6
-    frac = n_paths / args.steps / float(args.width * args.height * args.spp)
-    sample = "%d tiles of %dx%d px on a regular grid over the %dx%d frame (%.2f %% of its pixels), %d spp: %d paths per step" % (
+    frac = n_paths / args.steps / float(args.width * args.height * ref_spp)
+    sample = "%d tiles of %dx%d px on a regular grid over the %dx%d frame (%.2f %% of its pixels), %d of the %d spp: %d paths per step" % (
         len(tiles), tiles[0][2] - tiles[0][0], tiles[0][3] - tiles[0][1], args.width, args.height, 100.0 * frac,
-        args.spp, n_paths // args.steps)
+        ref_spp, args.spp, n_paths // args.steps)
     line = {
         "impl": "reference",
         "metric": "Mpaths/s (1080p, 1M tris, Standard Surface + Hosek sky, depth 10)",
