@@ -513,8 +513,9 @@ class Renderer:
         tlas_ms = C.c_float()
         _check(lib().fr_get_accel_info2(self._h, _u(out5), C.byref(tlas_ms)))
         return dict(n_faces=int(out[0]), n_nodes=int(out[1]), depth=int(out[2]), build_ms=ms.value,
-                    bytes=int(nbytes.value), two_level=bool(out5[0]), n_instances=int(out5[1]), n_meshes=int(out5[2]),
-                    n_stored_faces=int(out5[3]), tlas_update_ms=tlas_ms.value)
+                    bytes=int(nbytes.value), two_level=bool(out5[0] & 1), tlas_refitted=bool(out5[0] & 2),
+                    n_instances=int(out5[1]), n_meshes=int(out5[2]), n_stored_faces=int(out5[3]),
+                    tlas_update_ms=tlas_ms.value)
 
     ACCEL_MODES = {"auto": 0, "flat": 1, "two_level": 2}
 

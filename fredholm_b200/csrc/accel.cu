@@ -8,6 +8,7 @@
 #include <stdexcept>
 
 #include "bvh_build.h"
+#include "bvh_quant.cuh"
 
 namespace frd
 {
@@ -60,7 +61,137 @@ __global__ void k_instance_placeholders(const float* __restrict__ mesh_bounds, c
   indices[i] = make_uint3(3u * i, 3u * i + 1u, 3u * i + 2u);
 }
 
+// ---- instance-tree refit ----------------------------------------------------------------------------------
+constexpr int kRefitThreads = 1024;
+constexpr int kMaxRefitLevels = kSmemStack + kLocalStack;
+struct LevelTable {
+  uint32_t depth;
+  uint32_t begin[kMaxRefitLevels + 1];
+};
+
+// One block walks the instance tree bottom-up, level by level (nodes are numbered level by level, so a node's
+// inner children have already been fitted): child boxes from the refreshed placeholders or from the children's
+// node boxes, node box = their union, node frame and quantised child boxes rewritten in place.  Slot assignment
+// (octant order) and topology are those of the last rebuild.
+__global__ void __launch_bounds__(kRefitThreads) k_refit_tlas(Node8* __restrict__ nodes, float4* __restrict__ tris,
+                                                             const float3* __restrict__ placeholder_vertices, uint32_t n_inst,
+                                                             LevelTable lv, float* __restrict__ node_box, float* __restrict__ root_out)
+{
+  // the placeholders keep their place in the leaf order; only their boxes move
+  for (uint32_t j = threadIdx.x; j < n_inst; j += blockDim.x) {
+    const float4 v0 = tris[3ull * j], v1 = tris[3ull * j + 1];
+    const uint32_t id = __float_as_uint(v0.w);
+    const float3 lo = placeholder_vertices[3ull * id], hi = placeholder_vertices[3ull * id + 1];
+    tris[3ull * j] = make_float4(lo.x, lo.y, lo.z, v0.w);
+    tris[3ull * j + 1] = make_float4(hi.x, hi.y, hi.z, v1.w);
+    tris[3ull * j + 2] = make_float4(lo.x, hi.y, lo.z, 0.0f);
+  }
+  __threadfence_block();
+  __syncthreads();
+  for (int level = (int)lv.depth - 1; level >= 0; --level) {
+    for (uint32_t node = lv.begin[level] + threadIdx.x; node < lv.begin[level + 1]; node += blockDim.x) {
+      Node8 nd = nodes[node];
+      float clo[8][3], chi[8][3];
+      float nlo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, nhi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+      for (int s = 0; s < 8; ++s) {
+        const uint32_t m = nd.meta[s];
+        if (m == 0u) continue;
+        float lo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, hi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+        if ((m & 0x1fu) >= 24u) {
+          const uint32_t c = nd.child_base + __popc((uint32_t)nd.imask & ((1u << s) - 1u));
+          for (int a = 0; a < 3; ++a) {
+            lo[a] = node_box[6ull * c + a];
+            hi[a] = node_box[6ull * c + 3 + a];
+          }
+        } else {
+          const uint32_t cnt = __popc(m >> 5), off = m & 0x1fu;
+          for (uint32_t q = 0; q < cnt; ++q) {
+            const float4 a0 = tris[3ull * (nd.tri_base + off + q)], a1 = tris[3ull * (nd.tri_base + off + q) + 1];
+            lo[0] = fminf(lo[0], a0.x), lo[1] = fminf(lo[1], a0.y), lo[2] = fminf(lo[2], a0.z);
+            hi[0] = fmaxf(hi[0], a1.x), hi[1] = fmaxf(hi[1], a1.y), hi[2] = fmaxf(hi[2], a1.z);
+          }
+        }
+        for (int a = 0; a < 3; ++a) {
+          clo[s][a] = lo[a];
+          chi[s][a] = hi[a];
+          nlo[a] = fminf(nlo[a], lo[a]);
+          nhi[a] = fmaxf(nhi[a], hi[a]);
+        }
+      }
+      nd.px = nlo[0];
+      nd.py = nlo[1];
+      nd.pz = nlo[2];
+      const uint32_t ex = grid_exponent(__fsub_ru(nhi[0], nlo[0])), ey = grid_exponent(__fsub_ru(nhi[1], nlo[1])),
+                     ez = grid_exponent(__fsub_ru(nhi[2], nlo[2]));
+      nd.ex = (uint8_t)ex;
+      nd.ey = (uint8_t)ey;
+      nd.ez = (uint8_t)ez;
+      const float isx = grid_inverse_step(ex), isy = grid_inverse_step(ey), isz = grid_inverse_step(ez);
+      for (int s = 0; s < 8; ++s) {
+        if (nd.meta[s] == 0u) continue;
+        nd.qlox[s] = quantize_lo(clo[s][0], nlo[0], isx);
+        nd.qloy[s] = quantize_lo(clo[s][1], nlo[1], isy);
+        nd.qloz[s] = quantize_lo(clo[s][2], nlo[2], isz);
+        nd.qhix[s] = quantize_hi(chi[s][0], nlo[0], isx);
+        nd.qhiy[s] = quantize_hi(chi[s][1], nlo[1], isy);
+        nd.qhiz[s] = quantize_hi(chi[s][2], nlo[2], isz);
+      }
+      nodes[node] = nd;
+      for (int a = 0; a < 3; ++a) {
+        node_box[6ull * node + a] = nlo[a];
+        node_box[6ull * node + 3 + a] = nhi[a];
+      }
+    }
+    __threadfence_block();
+    __syncthreads();
+  }
+  if (threadIdx.x < 6) root_out[threadIdx.x] = node_box[threadIdx.x];
+}
+
+float half_area6(const float* b)
+{
+  const float ex = b[3] - b[0], ey = b[4] - b[1], ez = b[5] - b[2];
+  return ex * ey + ey * ez + ez * ex;
+}
+
 }  // namespace
+
+bool refit_tlas(cudaStream_t stream, const fredholm::Matrix3x4* d_o2w, TwoLevelBvh& out, float max_growth)
+{
+  const uint32_t n = out.n_instances;
+  const std::vector<uint32_t>& lb = out.tlas.level_begin;
+  if (n == 0 || lb.size() < 2 || lb.size() > (size_t)kMaxRefitLevels + 1 || out.rebuilt_root_area <= 0.0f) return false;
+  LevelTable lv;
+  lv.depth = (uint32_t)lb.size() - 1;
+  for (size_t k = 0; k < lb.size(); ++k) lv.begin[k] = lb[k];
+  out.refit_boxes.reserve(6ull * out.tlas.n_nodes);
+  out.refit_root.reserve(6);
+  cudaEvent_t e0, e1;
+  FR_CUDA_CHECK(cudaEventCreate(&e0));
+  FR_CUDA_CHECK(cudaEventCreate(&e1));
+  FR_CUDA_CHECK(cudaEventRecord(e0, stream));
+  k_instance_placeholders<<<(n + 127) / 128, 128, 0, stream>>>(out.mesh_bounds.get(), d_o2w, n, out.placeholder_vertices.get(),
+                                                               out.placeholder_indices.get());
+  FR_CUDA_LAUNCH_CHECK();
+  k_refit_tlas<<<1, kRefitThreads, 0, stream>>>(out.nodes.get(), out.tris.get(), out.placeholder_vertices.get(), n, lv,
+                                               out.refit_boxes.get(), out.refit_root.get());
+  FR_CUDA_LAUNCH_CHECK();
+  FR_CUDA_CHECK(cudaEventRecord(e1, stream));
+  float root[6];
+  FR_CUDA_CHECK(cudaMemcpyAsync(root, out.refit_root.get(), sizeof(root), cudaMemcpyDeviceToHost, stream));
+  FR_CUDA_CHECK(cudaStreamSynchronize(stream));
+  FR_CUDA_CHECK(cudaEventElapsedTime(&out.tlas_ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  for (int a = 0; a < 3; ++a) {
+    out.bounds_lo[a] = root[a];
+    out.bounds_hi[a] = root[3 + a];
+  }
+  out.last_update_was_refit = true;
+  // instances that have moved far apart leave a stale topology (siblings that no longer are neighbours): the tree
+  // is still correct, but the caller should rebuild it
+  return half_area6(root) <= max_growth * out.rebuilt_root_area;
+}
 
 void update_tlas(cudaStream_t stream, const fredholm::Matrix3x4* d_o2w, TwoLevelBvh& out)
 {
@@ -88,6 +219,9 @@ void update_tlas(cudaStream_t stream, const fredholm::Matrix3x4* d_o2w, TwoLevel
     out.bounds_lo[a] = out.tlas.bounds_lo[a];
     out.bounds_hi[a] = out.tlas.bounds_hi[a];
   }
+  const float root6[6] = {out.bounds_lo[0], out.bounds_lo[1], out.bounds_lo[2], out.bounds_hi[0], out.bounds_hi[1], out.bounds_hi[2]};
+  out.rebuilt_root_area = half_area6(root6);
+  out.last_update_was_refit = false;
   out.depth = out.tlas.depth + out.blas_depth;
   // TLAS levels + what enter_instance parks (3 entries) + BLAS levels must fit the traversal stack
   if (out.depth + 3 + 2 > (uint32_t)(kSmemStack + kLocalStack)) throw std::runtime_error("two-level bvh: tree too deep for the traversal stack");

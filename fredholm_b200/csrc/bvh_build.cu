@@ -10,6 +10,7 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_select.cuh>
 
+#include <algorithm>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -18,6 +19,7 @@
 #include <stdexcept>
 
 #include "bvh_build.h"
+#include "bvh_quant.cuh"
 
 namespace frd
 {
@@ -378,13 +380,6 @@ __device__ __forceinline__ float half_area(const float4& lo, const float4& hi)
   return ex * ey + ey * ez + ez * ex;
 }
 
-// biased exponent e such that extent <= 255 * 2^(e-127)
-__device__ __forceinline__ uint32_t grid_exponent(float extent)
-{
-  const float step = __fdiv_ru(extent, 255.0f);
-  uint32_t e = (__float_as_uint(step) + 0x007fffffu) >> 23;
-  return min(max(e, 1u), 254u);
-}
 
 struct CollapseCounters {
   uint32_t n_nodes;
@@ -512,8 +507,7 @@ __device__ void collapse_node(uint32_t n8, uint32_t* __restrict__ work, int n, c
   out.child_base = cbase;
   out.tri_base = tbase;
   // 1 / 2^(e-127) = 2^(127-e) -> biased exponent 254 - e
-  const float isx = __uint_as_float((254u - ex) << 23), isy = __uint_as_float((254u - ey) << 23),
-              isz = __uint_as_float((254u - ez) << 23);
+  const float isx = grid_inverse_step(ex), isy = grid_inverse_step(ey), isz = grid_inverse_step(ez);
   uint32_t rank = 0, toff = 0;
   for (int s = 0; s < 8; ++s) {
     const int k = child_at[s];
@@ -527,12 +521,12 @@ __device__ void collapse_node(uint32_t n8, uint32_t* __restrict__ work, int n, c
     const uint32_t cnt = tri_count(t, n, id);
     const float4 l = t.lo[id], h = t.hi[id];
     // conservative: lower bounds round down, upper bounds round up
-    out.qlox[s] = (uint8_t)fminf(fmaxf(floorf(__fmul_rd(__fsub_rd(l.x, nlo.x), isx)), 0.0f), 255.0f);
-    out.qloy[s] = (uint8_t)fminf(fmaxf(floorf(__fmul_rd(__fsub_rd(l.y, nlo.y), isy)), 0.0f), 255.0f);
-    out.qloz[s] = (uint8_t)fminf(fmaxf(floorf(__fmul_rd(__fsub_rd(l.z, nlo.z), isz)), 0.0f), 255.0f);
-    out.qhix[s] = (uint8_t)fminf(fmaxf(ceilf(__fmul_ru(__fsub_ru(h.x, nlo.x), isx)), 0.0f), 255.0f);
-    out.qhiy[s] = (uint8_t)fminf(fmaxf(ceilf(__fmul_ru(__fsub_ru(h.y, nlo.y), isy)), 0.0f), 255.0f);
-    out.qhiz[s] = (uint8_t)fminf(fmaxf(ceilf(__fmul_ru(__fsub_ru(h.z, nlo.z), isz)), 0.0f), 255.0f);
+    out.qlox[s] = quantize_lo(l.x, nlo.x, isx);
+    out.qloy[s] = quantize_lo(l.y, nlo.y, isy);
+    out.qloz[s] = quantize_lo(l.z, nlo.z, isz);
+    out.qhix[s] = quantize_hi(h.x, nlo.x, isx);
+    out.qhiy[s] = quantize_hi(h.y, nlo.y, isy);
+    out.qhiz[s] = quantize_hi(h.z, nlo.z, isz);
     if (cnt > (uint32_t)kLeafMax) {
       out.imask |= (uint8_t)(1u << s);
       out.meta[s] = (uint8_t)(0x20u | (24u + s));
@@ -568,8 +562,9 @@ __global__ void k_collapse(uint32_t level_begin, uint32_t level_end, uint32_t* _
 
 // small trees (an instance tree of a few thousand boxes): all levels in ONE launch of one block, which walks the
 // levels itself -- no host round trip per level.  depth_out receives the number of levels.
-constexpr int kCollapseSmallThreads = 256;
+constexpr int kCollapseSmallThreads = 1024;
 constexpr int kSmallTree = 16384;  // primitives
+constexpr int kMaxLevels = kSmemStack + kLocalStack;
 __global__ void __launch_bounds__(kCollapseSmallThreads) k_collapse_small(uint32_t* __restrict__ work, int n, Lbvh t,
                                                                          const float4* __restrict__ wtri,
                                                                          const uint32_t* __restrict__ sorted,
@@ -577,6 +572,7 @@ __global__ void __launch_bounds__(kCollapseSmallThreads) k_collapse_small(uint32
                                                                          Node8* __restrict__ nodes, float4* __restrict__ tris,
                                                                          uint32_t max_nodes, uint32_t* __restrict__ depth_out)
 {
+  // depth_out[0] = number of levels, depth_out[1 + k] = first node of level k, depth_out[1 + levels] = node count
   __shared__ uint32_t s_begin, s_end;
   if (threadIdx.x == 0) {
     s_begin = 0;
@@ -585,6 +581,7 @@ __global__ void __launch_bounds__(kCollapseSmallThreads) k_collapse_small(uint32
   __syncthreads();
   uint32_t depth = 0;
   while (s_begin < s_end && s_end <= max_nodes) {
+    if (threadIdx.x == 0 && depth < (uint32_t)kMaxLevels) depth_out[1 + depth] = s_begin;
     for (uint32_t n8 = s_begin + threadIdx.x; n8 < s_end; n8 += blockDim.x)
       collapse_node(n8, work, n, t, wtri, sorted, counters, nodes, tris);
     __threadfence_block();
@@ -596,7 +593,10 @@ __global__ void __launch_bounds__(kCollapseSmallThreads) k_collapse_small(uint32
     depth++;
     __syncthreads();
   }
-  if (threadIdx.x == 0) *depth_out = depth;
+  if (threadIdx.x == 0) {
+    depth_out[0] = depth;
+    if (depth <= (uint32_t)kMaxLevels) depth_out[1 + depth] = s_begin;
+  }
 }
 
 __global__ void k_empty_root(Node8* nodes)
@@ -658,9 +658,9 @@ namespace
 // cudaMallocFromPoolAsync) with the release threshold lifted, so a rebuild -- set_time on an animated scene --
 // reuses the pool's memory instead of paying cudaMalloc / cudaFree for every buffer (these calls were 20-90 ms
 // of a 52 M-triangle build).  The device's default pool, which the host application may share (e.g. PyTorch's
-// cudaMallocAsync backend), is never touched.  What the pool keeps between builds: nothing after the first
-// build of a device (static scenes give everything back), up to FRD_BVH_POOL_KEEP_GB (default 16) after a
-// rebuild.
+// cudaMallocAsync backend), is never touched.  What the pool keeps between builds: up to FRD_BVH_POOL_KEEP_GB
+// (default 16, 0 = give everything back), never more than a tenth of the device's memory -- mapping 10 GB of
+// fresh pool memory costs more than the 52 M-triangle build that uses it (1.7 s against 85 ms).
 thread_local cudaStream_t g_scratch_stream = nullptr;
 thread_local cudaMemPool_t g_scratch_pool = nullptr;
 
@@ -703,8 +703,10 @@ void trim_scratch_pool()
   if (!g_pools[dev]) return;
   const char* e = getenv("FRD_BVH_POOL_KEEP_GB");
   const size_t keep_gb = e ? (size_t)strtoull(e, nullptr, 0) : 16;
-  const size_t keep = g_builds[dev]++ == 0 ? 0 : keep_gb << 30;
-  cudaMemPoolTrimTo(g_pools[dev], keep);
+  size_t free_b = 0, total_b = 0;
+  if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) total_b = 0;
+  g_builds[dev]++;
+  cudaMemPoolTrimTo(g_pools[dev], std::min(keep_gb << 30, total_b / 10));
 }
 
 template <typename T>
@@ -858,17 +860,37 @@ void build_bvh_with(bool use_ploc, cudaStream_t stream, const float3* d_vertices
   FR_CUDA_CHECK(cudaMemcpyAsync(work.get(), &root_id, sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
   uint32_t begin = 0, end = 1, depth = 0;
   if (n <= kSmallTree) {
-    // instance trees and other small inputs: one launch, one read-back
-    ScratchBuf<uint32_t> d_depth(1);
+    // Instance trees and other small inputs: ONE launch for all levels and ONE host round trip for the whole
+    // build -- the node pool is copied at its capacity (a few hundred KB), so nothing has to be known on the host
+    // before the final synchronisation.  This is the per-frame cost of an animated two-level scene.
+    ScratchBuf<uint32_t> d_depth(kMaxLevels + 2);
     k_collapse_small<<<1, kCollapseSmallThreads, 0, stream>>>(work.get(), n, t, wtri.get(), tri_order, counters.get(), nodes.get(),
                                                                out.tris.get(), (uint32_t)max_nodes, d_depth.get());
     FR_CUDA_LAUNCH_CHECK();
-    CollapseCounters h;
-    FR_CUDA_CHECK(cudaMemcpyAsync(&h, counters.get(), sizeof(h), cudaMemcpyDeviceToHost, stream));
-    FR_CUDA_CHECK(cudaMemcpyAsync(&depth, d_depth.get(), sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    out.nodes.reserve(max_nodes);
+    FR_CUDA_CHECK(cudaMemcpyAsync(out.nodes.get(), nodes.get(), sizeof(Node8) * max_nodes, cudaMemcpyDeviceToDevice, stream));
+    struct {
+      CollapseCounters c;
+      uint32_t depth[kMaxLevels + 2];
+      float bounds[6];
+    } h;
+    FR_CUDA_CHECK(cudaMemcpyAsync(&h.c, counters.get(), sizeof(h.c), cudaMemcpyDeviceToHost, stream));
+    FR_CUDA_CHECK(cudaMemcpyAsync(h.depth, d_depth.get(), sizeof(h.depth), cudaMemcpyDeviceToHost, stream));
+    FR_CUDA_CHECK(cudaMemcpyAsync(h.bounds, bounds.get(), sizeof(h.bounds), cudaMemcpyDeviceToHost, stream));
     FR_CUDA_CHECK(cudaStreamSynchronize(stream));
-    if (h.n_nodes > max_nodes) throw std::runtime_error("bvh collapse: node pool overflow");
-    begin = end = h.n_nodes;
+    if (h.c.n_nodes > max_nodes) throw std::runtime_error("bvh collapse: node pool overflow");
+    out.depth = h.depth[0];
+    out.n_nodes = h.c.n_nodes;
+    out.level_begin.clear();
+    if (out.depth <= (uint32_t)kMaxLevels) out.level_begin.assign(h.depth + 1, h.depth + 2 + out.depth);
+    for (int a = 0; a < 3; ++a) {
+      out.bounds_lo[a] = h.bounds[a];
+      out.bounds_hi[a] = h.bounds[3 + a];
+    }
+    clk.mark("collapse+finish");
+    if (out.depth + 2 > (uint32_t)(kSmemStack + kLocalStack)) throw TreeTooDeep();
+    if (use_ploc && getenv("FRD_PLOC_FORCE_FALLBACK")) throw TreeTooDeep();  // test hook for the fallback path
+    return;
   }
   while (begin < end) {
     const uint32_t cnt = end - begin;
@@ -886,6 +908,7 @@ void build_bvh_with(bool use_ploc, cudaStream_t stream, const float3* d_vertices
   clk.mark("collapse");
   out.depth = depth;
   out.n_nodes = end;
+  out.level_begin.clear();
   // shrink the node pool to its final size
   out.nodes.reserve(end);
   FR_CUDA_CHECK(cudaMemcpyAsync(out.nodes.get(), nodes.get(), sizeof(Node8) * end, cudaMemcpyDeviceToDevice, stream));

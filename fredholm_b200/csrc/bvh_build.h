@@ -20,6 +20,9 @@ struct DeviceBvh {
   uint32_t n_faces = 0;
   uint32_t depth = 0;  // levels of the 8-wide tree
   uint32_t ploc_rounds = 0;  // merge rounds of the PLOC builder (0: LBVH)
+  // small trees (<= 16 Ki primitives, built in one launch): first node of every level, level_begin[depth] = n_nodes
+  // (nodes are numbered level by level) -- what a bottom-up refit walks
+  std::vector<uint32_t> level_begin;
   float bounds_lo[3] = {0, 0, 0}, bounds_hi[3] = {0, 0, 0};
 
   BvhView view() const
@@ -56,7 +59,11 @@ struct TwoLevelBvh {
   uint32_t n_nodes = 0;             // TLAS capacity + all BLAS nodes
   uint32_t n_blas_faces = 0;        // triangles stored (distinct meshes only)
   uint32_t blas_depth = 0, depth = 0;
-  float tlas_ms = 0.0f;             // device time of the last update_tlas
+  float tlas_ms = 0.0f;             // device time of the last update_tlas / refit_tlas
+  bool last_update_was_refit = false;
+  float rebuilt_root_area = 0.0f;   // half surface area of the TLAS root box at its last rebuild
+  DevBuf<float> refit_boxes;        // [6 per TLAS node] + [6 per instance] scratch of refit_tlas
+  DevBuf<float> refit_root;         // [6] root box of the last refit
   float bounds_lo[3] = {0, 0, 0}, bounds_hi[3] = {0, 0, 0};
   size_t bytes() const { return nodes.bytes() + tris.bytes() + instances.bytes(); }
   BvhView view(const fredholm::Matrix3x4* d_w2o) const
@@ -76,5 +83,11 @@ void build_two_level(cudaStream_t stream, const float3* d_vertices, const uint3*
                      const fredholm::Matrix3x4* d_o2w, TwoLevelBvh& out);
 // instance boxes from the current transforms + TLAS rebuild (radix tree).  Synchronises the stream.
 void update_tlas(cudaStream_t stream, const fredholm::Matrix3x4* d_o2w, TwoLevelBvh& out);
+// instance boxes from the current transforms + REFIT of the instance tree: the topology of the last rebuild is
+// kept, every node's child boxes are recomputed bottom-up and re-quantised in ONE launch (reference: the IAS
+// rebuild of Renderer::set_time, renderer.h:614-640).  Returns false (nothing done) when the tree has no level
+// table or has grown to more than `max_growth` times the surface area it had at its last rebuild -- the caller
+// rebuilds then.  Synchronises the stream.
+bool refit_tlas(cudaStream_t stream, const fredholm::Matrix3x4* d_o2w, TwoLevelBvh& out, float max_growth = 2.0f);
 
 }  // namespace frd

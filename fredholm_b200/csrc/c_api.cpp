@@ -318,7 +318,7 @@ int fr_get_accel_info2(fr_renderer* r, uint32_t* out5, float* tlas_update_ms)
 {
   return guarded([&] {
     const AccelInfo a = r->renderer.get_accel_info();
-    out5[0] = a.two_level ? 1u : 0u;
+    out5[0] = (a.two_level ? 1u : 0u) | (a.tlas_refitted ? 2u : 0u);
     out5[1] = a.n_instances;
     out5[2] = a.n_meshes;
     out5[3] = a.n_stored_faces;

@@ -339,6 +339,7 @@ void Renderer::Impl::refresh_accel_info(float build_ms)
     accel_info.n_meshes = bvh2.n_meshes;
     accel_info.n_stored_faces = bvh2.n_blas_faces;
     accel_info.tlas_update_ms = bvh2.tlas_ms;
+    accel_info.tlas_refitted = bvh2.last_update_was_refit;
   } else {
     accel_info.n_nodes = bvh.n_nodes;
     accel_info.depth = bvh.depth;
@@ -396,7 +397,10 @@ void Renderer::Impl::update_accel_after_transform_change()
 {
   upload_transforms();
   if (two_level && bvh2.n_instances == scene.m_transforms.size() && bvh2.n_instances > 0) {
-    frd::update_tlas(stream, d_o2w.get(), bvh2);
+    // refit the instance tree in place (one launch); rebuild it when the refit reports that the instances have
+    // spread out so much that the old topology is no longer a good one (or FRD_TLAS_REBUILD=1 asks for it)
+    const bool force_rebuild = getenv("FRD_TLAS_REBUILD") != nullptr;
+    if (force_rebuild || !frd::refit_tlas(stream, d_o2w.get(), bvh2)) frd::update_tlas(stream, d_o2w.get(), bvh2);
     refresh_accel_info(accel_info.build_ms);
     accel_valid = true;
   } else {

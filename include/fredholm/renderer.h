@@ -62,6 +62,7 @@ struct AccelInfo {
   bool two_level = false;
   uint32_t n_instances = 0, n_meshes = 0, n_stored_faces = 0;
   float tlas_update_ms = 0.0f;
+  bool tlas_refitted = false;  // the last update refitted the instance tree in place (else: rebuilt it)
 };
 
 // Acceleration-structure layout (extension).  FLAT: every instance's triangles in world space in ONE tree (fastest

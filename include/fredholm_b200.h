@@ -78,8 +78,10 @@ int fr_build_accel(fr_renderer* r);
 int fr_get_accel_info(fr_renderer* r, uint32_t* out3, float* build_ms, uint64_t* bytes);
 /* acceleration-structure layout (extension): 0 = auto, 1 = flat world-space tree, 2 = two-level (one object-space
  * tree per distinct mesh + an instance tree, like the reference's GAS + IAS, renderer.h:434-552); takes effect at the
- * next fr_build_accel.  fr_get_accel_info2: out5 = two_level, instances, distinct meshes, triangles stored, nodes;
- * tlas_update_ms = device time of the last instance-tree update (fr_set_time / fr_set_transforms in two-level mode) */
+ * next fr_build_accel.  fr_get_accel_info2: out5 = flags (bit 0 two-level, bit 1 the last instance-tree update was
+ * a refit in place), instances, distinct meshes, triangles stored, nodes; tlas_update_ms = device time of the last
+ * instance-tree update (fr_set_time / fr_set_transforms in two-level mode: a one-launch bottom-up refit, or a
+ * rebuild when the instances have spread so far that the refit asks for one) */
 int fr_set_accel_mode(fr_renderer* r, int mode);
 int fr_get_accel_info2(fr_renderer* r, uint32_t* out5, float* tlas_update_ms);
 /* structure inspection (tests / tools): copies the n_nodes 80-byte CWBVH nodes and the n_faces

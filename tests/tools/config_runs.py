@@ -160,7 +160,7 @@ def c4():
     info2 = r.accel_info()
     r.set_resolution(W, H)
     lay = DeviceLayers(W, H, names=("beauty", "depth"))
-    timed_render(r, cam, (1, 1, 1), lay, 4, 16)
+    timed_render(r, cam, (1, 1, 1), lay, 16, 16)       # warm-up at the measured wave size (allocations)
     ms, res = timed_render(r, cam, (1, 1, 1), lay, 16, 16, reps=2)
     img = lay.download("beauty")
     dep = lay.download("depth")

@@ -12,7 +12,7 @@ for mode in ("two_level", "flat"):
     info = r.accel_info()
     r.set_resolution(W, H)
     lay = DeviceLayers(W, H, names=("beauty",))
-    r.render(cam, (1, 1, 1), lay, 4, 16); r.wait()
+    r.render(cam, (1, 1, 1), lay, 16, 16); r.wait()
     r.set_stage_timing(True); r.stage_times(); r.reset_statistics()
     e0 = r.record_event(); lay.clear(); r.init_render_states(); r.render(cam, (1, 1, 1), lay, 16, 16); e1 = r.record_event(); r.wait()
     ms = api.event_elapsed_ms(e0, e1); st = r.statistics(); stages = r.stage_times()
