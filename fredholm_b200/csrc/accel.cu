@@ -193,7 +193,7 @@ bool refit_tlas(cudaStream_t stream, const fredholm::Matrix3x4* d_o2w, TwoLevelB
   return half_area6(root) <= max_growth * out.rebuilt_root_area;
 }
 
-void update_tlas(cudaStream_t stream, const fredholm::Matrix3x4* d_o2w, TwoLevelBvh& out)
+void update_tlas(cudaStream_t stream, const fredholm::Matrix3x4* d_o2w, TwoLevelBvh& out, int builder)
 {
   const uint32_t n = out.n_instances;
   if (n == 0) throw std::runtime_error("two-level bvh: no instances");
@@ -204,9 +204,8 @@ void update_tlas(cudaStream_t stream, const fredholm::Matrix3x4* d_o2w, TwoLevel
   k_instance_placeholders<<<(n + 127) / 128, 128, 0, stream>>>(out.mesh_bounds.get(), d_o2w, n, out.placeholder_vertices.get(),
                                                                out.placeholder_indices.get());
   FR_CUDA_LAUNCH_CHECK();
-  // radix tree: no merge rounds, a handful of launches -- this is the per-frame cost of an animated scene
   build_bvh(stream, out.placeholder_vertices.get(), out.placeholder_indices.get(), out.zeros.get(), nullptr, out.identity.get(), n,
-            out.tlas, /*builder=*/0);
+            out.tlas, builder);
   if (out.tlas.n_nodes > out.tlas_node_capacity) throw std::runtime_error("two-level bvh: TLAS exceeds its reserved node range");
   FR_CUDA_CHECK(cudaMemcpyAsync(out.nodes.get(), out.tlas.nodes.get(), sizeof(Node8) * out.tlas.n_nodes, cudaMemcpyDeviceToDevice, stream));
   FR_CUDA_CHECK(cudaMemcpyAsync(out.tris.get(), out.tlas.tris.get(), sizeof(float4) * 3ull * n, cudaMemcpyDeviceToDevice, stream));
@@ -301,7 +300,7 @@ void build_two_level(cudaStream_t stream, const float3* d_vertices, const uint3*
   out.placeholder_vertices.reserve(3ull * n_inst);
   out.placeholder_indices.reserve(n_inst);
   FR_CUDA_CHECK(cudaStreamSynchronize(stream));  // blas[] and the host vectors go out of scope
-  update_tlas(stream, d_o2w, out);
+  update_tlas(stream, d_o2w, out, /*builder=*/-1);  // first build: the default (PLOC) builder
 }
 
 }  // namespace frd

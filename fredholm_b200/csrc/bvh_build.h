@@ -82,7 +82,9 @@ void build_two_level(cudaStream_t stream, const float3* d_vertices, const uint3*
                      const std::vector<std::vector<uint32_t>>* face_flags_of_mesh,
                      const fredholm::Matrix3x4* d_o2w, TwoLevelBvh& out);
 // instance boxes from the current transforms + TLAS rebuild (radix tree).  Synchronises the stream.
-void update_tlas(cudaStream_t stream, const fredholm::Matrix3x4* d_o2w, TwoLevelBvh& out);
+// builder: 0 = radix tree (a handful of launches: the choice for a rebuild between frames), 1 / -1 = PLOC
+// (better tree, ~1 ms of merge rounds: the choice for the first build)
+void update_tlas(cudaStream_t stream, const fredholm::Matrix3x4* d_o2w, TwoLevelBvh& out, int builder = 0);
 // instance boxes from the current transforms + REFIT of the instance tree: the topology of the last rebuild is
 // kept, every node's child boxes are recomputed bottom-up and re-quantised in ONE launch (reference: the IAS
 // rebuild of Renderer::set_time, renderer.h:614-640).  Returns false (nothing done) when the tree has no level
