@@ -27,3 +27,47 @@ for name, s, cam_def, lights in (("cornell", scenes.cornell_box(), scenes.CORNEL
     ids, _ = r.trace_closest(rays)
     print("  batch hits", int((ids[:, 0] != 0xffffffff).sum()))
 r.close()
+
+# ---- round 2: two-level structure (instances, refit + rebuild), wave overlap, sample groups, GPU mesh preparation,
+#      sharded render with a one-rank communicator ----
+import os, tempfile
+s = scenes.instanced_scene(n_instances=40, mesh_res=(12, 6), terrain_res=16)
+r = Renderer(0)
+r.set_accel_mode("two_level")
+r.set_scene(s)
+r.build_accel()
+c = scenes.INSTANCED_CAMERA
+cam = Camera(api.camera_walk(c["origin"], 0.0, 100.0, 0, 0.0), c["fov"], c["F"], c["focus"])
+W, H = 96, 64
+r.set_resolution(W, H)
+lay = DeviceLayers(W, H)
+r.set_samples_per_warp(4)
+r.set_wave_overlap(True)
+r.set_max_wave_paths(2 * ((W + 3) // 4) * ((H + 1) // 2) * 32)      # two waves of one 4-sample group in flight
+r.render(cam, (1, 1, 1), lay, 8, 6)
+r.wait()
+tr = s.transforms.copy().reshape(-1, 4, 4)
+tr[3, 3, 1] += 4.0
+r.set_transforms(tr.reshape(-1, 16))                                  # refit
+tr[1:, 3, 0] *= 9.0
+r.set_transforms(tr.reshape(-1, 16))                                  # scattered: rebuild
+info = r.accel_info()
+lay.clear(); r.init_render_states()
+r.render(cam, (1, 1, 1), lay, 4, 6)
+r.wait()
+rays = np.random.default_rng(2).normal(size=(5000, 6)).astype(np.float32) * np.array([60, 10, 60, 1, 1, 1], np.float32)
+ids, _ = r.trace_closest(rays)
+print("two-level", info["two_level"], info["tlas_refitted"], float(lay.download("beauty")[..., :3].mean()), int((ids[:, 0] != 0xffffffff).sum()))
+r.comm_init(api.comm_unique_id(), 0, 1)
+lay.clear(); r.init_render_states()
+r.render_sharded(cam, (1, 1, 1), lay, 16, 4)
+r.wait()
+print("sharded", float(lay.download("beauty")[..., :3].mean()))
+r.comm_destroy()
+r.close()
+with tempfile.TemporaryDirectory() as tmp:
+    os.environ["FRD_GPU_MESH_PREP"] = "1"
+    for attrs in (True, False):
+        p = scenes.write_obj(scenes.standard_surface_scene(24, 12, sphere_res=(8, 4)), tmp, "m%d" % attrs, with_attributes=attrs)
+        sc = api.Scene(); sc.load_model(p); a = sc.arrays()
+        print("mesh prep", attrs, a.n_faces, len(a.vertices))
