@@ -109,3 +109,31 @@ def test_scene_object_path_equals_arrays(renderer, tmp_path):
     sc.close()
     assert np.array_equal(a, b)
     assert a.mean() > 0.01
+
+
+def test_invalid_input_is_rejected_and_the_renderer_stays_usable(renderer):
+    """Round-2 hardening: a scene with an out-of-range index never reaches the device (Scene::validate in
+    upload_scene), max_depth beyond the Sobol table is refused, and the renderer keeps working afterwards."""
+    import copy
+    good = scenes.cornell_box()
+    bad = copy.deepcopy(good)
+    bad.indices[5, 2] = len(bad.vertices) + 7
+    with pytest.raises(api.FredholmError, match="invalid scene: vertex index out of range"):
+        renderer.set_scene(bad)
+    bad = copy.deepcopy(good)
+    bad.materials["normalmap_texture_id"][0] = 3          # no textures in this scene
+    with pytest.raises(api.FredholmError, match="invalid scene: texture id 3 out of range"):
+        renderer.set_scene(bad)
+    renderer.set_scene(good)
+    renderer.build_accel()
+    W = H = 32
+    renderer.set_resolution(W, H)
+    c = scenes.CORNELL_CAMERA
+    cam = Camera(api.camera_walk(c["origin"], 0.0, 0.0, 0, 0.0), c["fov"], c["F"], c["focus"])
+    lay = DeviceLayers(W, H, names=("beauty",))
+    with pytest.raises(api.FredholmError, match="max_depth must be <= 255"):
+        renderer.render(cam, (0, 0, 0), lay, 1, 256)
+    renderer.render(cam, (0, 0, 0), lay, 4, 255)          # the deepest path the sampler table supports
+    renderer.wait()
+    img = lay.download("beauty")
+    assert np.isfinite(img).all() and img[..., :3].mean() > 0.01
