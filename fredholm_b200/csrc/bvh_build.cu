@@ -144,6 +144,10 @@ struct Lbvh {
   uint32_t* visit;     // [n-1]
   const uint32_t* leaf_pos;  // [n] position of sorted leaf j in the triangle order the collapse reads
                              // (null: the Morton order itself, LBVH)
+  // SAH-cost collapse (optional, null = greedy largest-area-first): per internal node, the split of j slots
+  // between its two children (j = 2..8, 3 bits each, bits 0..20) and, for i = 2..7, whether i slots are no better
+  // than i - 1 (bits 21..26)
+  const uint32_t* sah_decision;
 };
 
 __device__ __forceinline__ int delta(const uint64_t* keys, int n, int i, int j)
@@ -381,6 +385,79 @@ __device__ __forceinline__ float half_area(const float4& lo, const float4& hi)
 }
 
 
+// ---- stage 5a (optional): which children an 8-wide node should get, by SAH cost ---------------------------
+// Ylitie, Karras, Laine 2017, section 4.1: c(n, i) = cheapest way to represent the binary sub-tree n as a
+// forest of at most i 8-wide sub-trees,
+//   c(n, 1) = A(n) P(n) c_tri                       if n fits a leaf slot (P <= kLeafMax)
+//           = A(n) c_node + dist(n, 8)              otherwise (n becomes an 8-wide node)
+//   c(n, i) = min(dist(n, i), c(n, i - 1)),         dist(n, j) = min_k c(left, k) + c(right, j - k)
+// computed bottom-up (second thread to arrive at a node does it); the collapse then follows the recorded splits
+// instead of opening the child with the largest area.  c_tri / c_node is the measured cost ratio of a triangle
+// test and a node visit in issue slots (13.3 vs 10.2 warp-instructions on the bench frame: the triangle phase runs
+// with few lanes); FRD_SAH_CT overrides it.
+struct SahDp {
+  float* cost;         // [8 per internal node], entries 1..7
+  uint32_t* decision;  // [internal nodes]
+  uint32_t* arrive;    // [internal nodes], zeroed
+  float c_tri;
+};
+
+__global__ void k_sah_dp(int n, Lbvh t, SahDp dp)
+{
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n || n < 2) return;
+  uint32_t cur = t.parent[(uint32_t)(n - 1 + j)];
+  for (;;) {
+    __threadfence();
+    if (atomicAdd(&dp.arrive[cur], 1u) == 0u) return;  // sibling not done yet
+    const uint2 ch = t.child[cur];
+    float cl[8], cr[8];
+    const volatile float* vc = dp.cost;
+    for (int side = 0; side < 2; ++side) {
+      const uint32_t c = side == 0 ? ch.x : ch.y;
+      float* dst = side == 0 ? cl : cr;
+      if (c >= (uint32_t)(n - 1)) {
+        const float a = half_area(t.lo[c], t.hi[c]) * dp.c_tri;
+        for (int i = 1; i < 8; ++i) dst[i] = a;
+      } else {
+        for (int i = 1; i < 8; ++i) dst[i] = vc[8ull * c + i];
+      }
+    }
+    const float area = half_area(t.lo[cur], t.hi[cur]);
+    const uint32_t P = tri_count(t, n, cur);
+    float dist[9];
+    uint32_t decision = 0;
+    for (int jj = 2; jj <= 8; ++jj) {
+      float best = 3.0e38f;
+      int best_k = 1;
+      for (int k = 1; k < jj; ++k) {
+        if (k > 7 || jj - k > 7) continue;
+        const float v = cl[k] + cr[jj - k];
+        if (v < best) {
+          best = v;
+          best_k = k;
+        }
+      }
+      dist[jj] = best;
+      decision |= (uint32_t)best_k << (3 * (jj - 2));
+    }
+    float c[8];
+    c[1] = P <= (uint32_t)kLeafMax ? area * (float)P * dp.c_tri : area + dist[8];
+    for (int i = 2; i <= 7; ++i) {
+      if (dist[i] < c[i - 1]) {
+        c[i] = dist[i];
+      } else {
+        c[i] = c[i - 1];
+        decision |= 1u << (21 + (i - 2));
+      }
+    }
+    for (int i = 1; i < 8; ++i) dp.cost[8ull * cur + i] = c[i];
+    dp.decision[cur] = decision;
+    if (cur == 0) return;
+    cur = t.parent[cur];
+  }
+}
+
 struct CollapseCounters {
   uint32_t n_nodes;
   uint32_t n_tris;
@@ -405,7 +482,40 @@ __device__ void collapse_node(uint32_t n8, uint32_t* __restrict__ work, int n, c
     c[0] = ch.x;
     c[1] = ch.y;
     nc = 2;
-    while (nc < 8) {
+    if (t.sah_decision) {
+      // follow the splits recorded by k_sah_dp: (node, slots) pairs on a small stack
+      nc = 0;
+      uint32_t st_node[16];
+      int st_slots[16];
+      int sp = 0;
+      st_node[sp] = b2;
+      st_slots[sp++] = 8;
+      bool root = true;
+      while (sp > 0) {
+        const uint32_t m = st_node[--sp];
+        int i = st_slots[sp];
+        const bool is_binary_leaf = m >= (uint32_t)(n - 1);
+        uint32_t d = 0;
+        if (!is_binary_leaf) {
+          d = t.sah_decision[m];
+          if (!root)
+            while (i > 1 && (d >> (21 + (i - 2))) & 1u) i--;
+        }
+        if (is_binary_leaf || (i == 1 && !root)) {
+          c[nc++] = m;
+          continue;
+        }
+        root = false;
+        const int k = (int)((d >> (3 * (i - 2))) & 7u);
+        const uint2 mc = t.child[m];
+        // right first so that the left sub-tree is emitted first
+        st_node[sp] = mc.y;
+        st_slots[sp++] = i - k;
+        st_node[sp] = mc.x;
+        st_slots[sp++] = k;
+      }
+    }
+    while (!t.sah_decision && nc < 8) {
       int best = -1;
       float best_area = -1.0f;
       for (int k = 0; k < nc; ++k) {
@@ -623,6 +733,20 @@ bool builder_is_ploc()
 {
   const char* e = getenv("FRD_BVH_BUILDER");
   return !(e && strcmp(e, "lbvh") == 0);
+}
+// k_sah_dp chooses the children of the 8-wide nodes (FRD_COLLAPSE=greedy: largest area first, the round-1 rule);
+// FRD_SAH_CT = cost of a triangle test relative to a node visit.  Measured on the bench frame
+// (profiles/r2j_collapse_sah.txt): 1.0 is the flat optimum, 0.3 ... 1.5 all beat the greedy rule.
+bool collapse_by_sah()
+{
+  const char* e = getenv("FRD_COLLAPSE");
+  return !(e && strcmp(e, "greedy") == 0);
+}
+float sah_tri_cost()
+{
+  const char* e = getenv("FRD_SAH_CT");
+  const float v = e ? (float)atof(e) : 1.0f;
+  return v > 0.0f ? v : 1.0f;
 }
 int ploc_radius()
 {
@@ -848,6 +972,19 @@ void build_bvh_with(bool use_ploc, cudaStream_t stream, const float3* d_vertices
   }
 
   clk.mark("binary");
+  // optional: choose the children of every 8-wide node by SAH cost instead of largest-area-first
+  ScratchBuf<float> sah_cost;
+  ScratchBuf<uint32_t> sah_decision, sah_arrive;
+  if (n > 2 && collapse_by_sah()) {
+    sah_cost.alloc(8ull * n_int);
+    sah_decision.alloc(n_int);
+    sah_arrive.alloc(n_int);
+    sah_arrive.zero(stream);
+    k_sah_dp<<<G, B, 0, stream>>>(n, t, SahDp{sah_cost.get(), sah_decision.get(), sah_arrive.get(), sah_tri_cost()});
+    FR_CUDA_LAUNCH_CHECK();
+    t.sah_decision = sah_decision.get();
+    clk.mark("sah dp");
+  }
   // collapse, level by level; node n8 is built from binary node work[n8]
   const size_t max_nodes = (size_t)n / 2 + 2;
   ScratchBuf<Node8> nodes(max_nodes);

@@ -9,6 +9,7 @@ ap.add_argument("--spp", type=int, default=16)
 ap.add_argument("--depth", type=int, default=10)
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--wave", type=int, default=0)
+ap.add_argument("--count", action="store_true", help="also one frame with the traversal counters")
 a = ap.parse_args()
 s = scenes.standard_surface_scene()
 L = scenes.STANDARD_LIGHTING; C = scenes.STANDARD_CAMERA
@@ -40,3 +41,11 @@ for _ in range(a.reps):
 e1 = r.record_event(); r.wait()
 ms = api.event_elapsed_ms(e0, e1) / a.reps
 print("untimed-stages frame %.2f ms  %.1f Mpaths/s  %.1f Mrays/s" % (ms, st["paths"] / a.reps / ms / 1e3, st["rays"] / a.reps / ms / 1e3))
+if a.count:
+    r.set_traversal_counting(True); r.reset_statistics(); r.init_render_states()
+    r.render(cam, (0, 0, 0), lay, a.spp, a.depth); r.wait()
+    st = r.statistics(); tc = r.traversal_counters(); r.set_traversal_counting(False)
+    for k in ("radiance", "shadow", "light"):
+        nr = max(1, st["rays_" + k])
+        if k == "shadow" and tc["light"][0] == 0: nr += st["rays_light"]  # no emitters: MIS rays are visibility rays
+        print("  %-8s %.2f nodes/ray  %.2f tris/ray" % (k, tc[k][0] / nr, tc[k][1] / nr))
