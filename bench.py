@@ -70,7 +70,7 @@ def parse_args():
     ap.add_argument("--small-scene", action="store_true", help="131k-triangle variant (debugging only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--wave-paths", type=int, default=0,
-                    help="paths in flight per wave (default: the whole frame, spp x tiled pixels)")
+                    help="paths in flight per wave (default: 16 samples x tiled pixels)")
     ap.add_argument("--strong-spp", type=int, default=STRONG_SPP,
                     help="total samples of the strong-scaling sub-record (BASELINE config 3); 0 skips it")
     return ap.parse_args()
@@ -540,10 +540,14 @@ def slots_per_sample(W, H):
     return ((W + 7) // 8) * ((H + 3) // 4) * 32
 
 
+WAVE_SPP = 16
+
+
 def wave_paths(args):
-    """All samples of the frame in ONE wave unless overridden: fewer, larger launches (the
-    persistent kernels have a fixed tail per launch) at the price of HBM for the wave state."""
-    return args.wave_paths or slots_per_sample(args.width, args.height) * args.spp
+    """Waves of 16 samples unless overridden.  With wave compaction (the stragglers of the four waves of a frame
+    finish their late bounces together) that is 12.7 GB of wave state at 2 % below the throughput of the whole
+    frame in ONE wave, which holds 35.6 GB (--wave-paths 132710400; profiles/r2k_wave_sweep.jsonl)."""
+    return args.wave_paths or slots_per_sample(args.width, args.height) * min(args.spp, WAVE_SPP)
 
 
 def main():

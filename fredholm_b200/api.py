@@ -107,6 +107,7 @@ SIGNATURES = {
     "fr_set_film_mode": (C.c_int, [_vp, C.c_int]),
     "fr_set_max_wave_paths": (C.c_int, [_vp, C.c_uint64]),
     "fr_set_wave_overlap": (C.c_int, [_vp, C.c_int]),
+    "fr_set_wave_compaction": (C.c_int, [_vp, C.c_int, C.c_uint32]),
     "fr_get_wave_state_bytes": (C.c_uint64, [_vp]),
     "fr_set_single_launch": (C.c_int, [_vp, C.c_int]),
     "fr_render": (C.c_int, [_vp, _fp, C.c_float, C.c_float, C.c_float, _fp, C.POINTER(_Layers), C.c_uint32,
@@ -698,6 +699,10 @@ class Renderer:
 
     def set_wave_overlap(self, on=True):
         _check(lib().fr_set_wave_overlap(self._h, 1 if on else 0))
+
+    def set_wave_compaction(self, on=True, depth=0):
+        """Stragglers of several waves finish their late bounces together (default on; depth 0 = after 3 bounces)."""
+        _check(lib().fr_set_wave_compaction(self._h, 1 if on else 0, int(depth)))
 
     def wave_state_bytes(self):
         return int(lib().fr_get_wave_state_bytes(self._h))

@@ -604,6 +604,10 @@ int fr_set_wave_overlap(fr_renderer* r, int on)
 {
   return guarded([&] { r->renderer.set_wave_overlap(on != 0); });
 }
+int fr_set_wave_compaction(fr_renderer* r, int on, uint32_t depth)
+{
+  return guarded([&] { r->renderer.set_wave_compaction(on != 0, depth ? depth : 3u); });
+}
 uint64_t fr_get_wave_state_bytes(fr_renderer* r) { return r ? (uint64_t)r->renderer.get_wave_state_bytes() : 0; }
 int fr_set_traversal_counting(fr_renderer* r, int on)
 {

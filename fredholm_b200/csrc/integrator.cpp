@@ -24,6 +24,7 @@ Integrator::Integrator(cudaStream_t stream) : m_stream(stream)
   m_sort_bits = std::min(std::max(env_u32("FRD_SORT_BITS", 4u), 1u), 7u);
   set_samples_per_warp(env_u32("FRD_SAMPLES_PER_WARP", kDefaultSamplesPerWarp));
   m_overlap = env_u32("FRD_WAVE_OVERLAP", 0u) != 0u;
+  set_wave_compaction(env_u32("FRD_WAVE_COMPACTION", 1u) != 0u, env_u32("FRD_WAVE_COMPACTION_DEPTH", kDefaultCompactionDepth));
 }
 
 void Integrator::set_samples_per_warp(uint32_t spw)
@@ -66,6 +67,8 @@ Integrator::~Integrator()
   }
   for (auto e : m_event_pool) cudaEventDestroy(e);
   if (m_ev_start) cudaEventDestroy(m_ev_start);
+  if (m_ev_alive) cudaEventDestroy(m_ev_alive);
+  if (m_alive_host) cudaFreeHost(m_alive_host);
   for (auto e : m_ev_film)
     if (e) cudaEventDestroy(e);
   if (m_aux_stream) {
@@ -131,13 +134,13 @@ StageTimes Integrator::stage_times()
 }
 
 // ---- wave sets -------------------------------------------------------------------------------------------
-void Integrator::WaveSet::grow_core(size_t n_slots)
+void Integrator::WaveSet::grow_core(size_t n_slots, size_t l_slots)
 {
   ray_o.alloc(n_slots);
   ray_d.alloc(n_slots);
   hit.alloc(n_slots);
   thr.alloc(n_slots);
-  L.alloc(n_slots);
+  L.alloc(l_slots);
   queue[0].alloc(n_slots);
   queue[1].alloc(n_slots);
   shadow[1].alloc(n_slots);
@@ -151,6 +154,7 @@ void Integrator::WaveSet::grow_core(size_t n_slots)
   shadow[2].release();
   sort_keys.release();
   sort_out.release();
+  origin.release();
 }
 
 void Integrator::WaveSet::release()
@@ -170,13 +174,15 @@ void Integrator::WaveSet::release()
   light.release();
   sort_keys.release();
   sort_out.release();
+  origin.release();
   capacity = 0;
+  L_capacity = 0;
 }
 
 size_t Integrator::WaveSet::bytes() const
 {
   size_t b = ray_o.bytes() + ray_d.bytes() + hit.bytes() + thr.bytes() + L.bytes() + aov0.bytes() + aov1.bytes() + aov2.bytes() +
-             queue[0].bytes() + queue[1].bytes() + light.bytes() + sort_keys.bytes() + sort_out.bytes();
+             queue[0].bytes() + queue[1].bytes() + light.bytes() + sort_keys.bytes() + sort_out.bytes() + origin.bytes();
   for (const auto& s : shadow) b += s.bytes();
   for (const auto& q : class_queue) b += q.bytes();
   return b;
@@ -201,14 +207,17 @@ WaveBuffers Integrator::WaveSet::view() const
   wb.ctl = ctl.get();
   wb.first_hit = nullptr;
   wb.pix_aov0 = wb.pix_aov1 = wb.pix_aov2 = nullptr;
+  wb.origin = nullptr;  // set by the caller for a straggler set
+  wb.origin_stride = wb.origin_samples = 0;
   return wb;
 }
 
 // Core buffers for n_slots paths plus the optional ones this render needs -- the first-hit AOV words (48 B / path),
 // the sun and area-light NEE queues (48 B / path each), the coherence-sort scratch (8 B / path): a beauty-only
 // render of a scene without emitters keeps 268 B / path instead of 372.
-void Integrator::ensure_capacity(WaveSet& set, size_t n_slots, const WaveNeeds& need)
+void Integrator::ensure_capacity(WaveSet& set, size_t n_slots, const WaveNeeds& need, size_t l_slots, bool with_origin)
 {
+  l_slots = std::max(l_slots, n_slots);
   if (set.ctl.size() == 0) {
     set.ctl.alloc(1);
     set.ctl.zero(m_stream);
@@ -226,12 +235,17 @@ void Integrator::ensure_capacity(WaveSet& set, size_t n_slots, const WaveNeeds& 
     // everything instead of launching on a half-grown set.
     set.capacity = 0;
     try {
-      set.grow_core(n_slots);
+      set.grow_core(n_slots, std::max(l_slots, set.L_capacity));
     } catch (...) {
       set.release();
       throw;
     }
     set.capacity = n_slots;
+    set.L_capacity = std::max(l_slots, set.L_capacity);
+  } else if (l_slots > set.L_capacity) {
+    sync_once();
+    set.L.alloc(l_slots);
+    set.L_capacity = l_slots;
   }
   auto grow = [&](auto& buf, bool wanted) {
     if (!wanted || buf.size() >= set.capacity) return;
@@ -245,6 +259,7 @@ void Integrator::ensure_capacity(WaveSet& set, size_t n_slots, const WaveNeeds& 
   grow(set.shadow[2], need.area_queue);
   grow(set.sort_keys, need.sort);
   grow(set.sort_out, need.sort);
+  grow(set.origin, with_origin);
   m_state_bytes = m_set[0].bytes() + m_set[1].bytes();
 }
 
@@ -254,11 +269,32 @@ void Integrator::render_wave(cudaStream_t s, WaveSet& set, const WaveBuffers& wb
                              uint32_t class_mask)
 {
   FR_NVTX_RANGE("wave");
+  start_wave(s, wb, wp);
+  run_bounces(s, set, wb, wp, scene, class_mask, 0, wp.max_depth);
+}
+
+void Integrator::start_wave(cudaStream_t s, const WaveBuffers& wb, const WaveParams& wp)
+{
   stage(s, STAGE_ADVANCE, [&] {
     launch_wave_begin(s, wb, (unsigned long long)wp.n_samples * wp.film.width * wp.film.height);
   });
   stage(s, STAGE_GENERATE, [&] { launch_generate(s, wp, wb); });
-  for (uint32_t depth = 0; depth < wp.max_depth; ++depth) {
+}
+
+void Integrator::ensure_aux_stream()
+{
+  if (m_aux_stream) return;
+  FR_CUDA_CHECK(cudaStreamCreateWithFlags(&m_aux_stream, cudaStreamNonBlocking));
+  FR_CUDA_CHECK(cudaEventCreateWithFlags(&m_ev_start, cudaEventDisableTiming));
+  for (auto& e : m_ev_film) FR_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  FR_CUDA_CHECK(cudaEventCreateWithFlags(&m_ev_alive, cudaEventDisableTiming));
+  FR_CUDA_CHECK(cudaHostAlloc(reinterpret_cast<void**>(&m_alive_host), sizeof(uint32_t), cudaHostAllocDefault));
+}
+
+void Integrator::run_bounces(cudaStream_t s, WaveSet& set, const WaveBuffers& wb, const WaveParams& wp, const SceneView& scene,
+                             uint32_t class_mask, uint32_t depth_begin, uint32_t depth_end, bool probe_alive)
+{
+  for (uint32_t depth = depth_begin; depth < depth_end; ++depth) {
 #if FR_HAVE_NVTX
     char bounce_name[24];
     snprintf(bounce_name, sizeof(bounce_name), "bounce %u", depth);
@@ -277,6 +313,12 @@ void Integrator::render_wave(cudaStream_t s, WaveSet& set, const WaveBuffers& wb
     if (depth == 0) stage(s, STAGE_SHADE, [&] { launch_miss(s, wp, scene, wb); });
     for (int c = 0; c < CLS_MISS; ++c)
       if (class_mask & (1u << c)) stage(s, STAGE_SHADE, [&] { launch_shade(s, wp, scene, wb, depth, c); });
+    if (probe_alive && depth + 1 == depth_end) {
+      FR_CUDA_CHECK(cudaEventRecord(m_ev_start, s));
+      FR_CUDA_CHECK(cudaStreamWaitEvent(m_aux_stream, m_ev_start, 0));
+      FR_CUDA_CHECK(cudaMemcpyAsync(m_alive_host, &wb.ctl->n[Q_NEXT], sizeof(uint32_t), cudaMemcpyDeviceToHost, m_aux_stream));
+      FR_CUDA_CHECK(cudaEventRecord(m_ev_alive, m_aux_stream));
+    }
     if (scene.has_dir_light) {
       sort_queue(2u, SORT_SHADOW0, false);  // all sun rays point the same way
       stage(s, STAGE_TRACE_SHADOW, [&] { launch_trace_shadow(s, scene, wb, 0, order, depth == 0); });
@@ -310,12 +352,42 @@ void Integrator::render(const SceneView& scene, const fredholm::CameraParams& ca
   // paths in flight = whole sample groups (spw samples of every pixel), at least one
   const size_t groups_total = film_groups(film, n_samples);
   size_t groups_in_flight = std::max<size_t>(1, std::min<size_t>(groups_total, m_max_wave_paths / film.slots_per_group));
+  // wave compaction: a pass of up to kMaxWavesPerPass waves keeps all their radiance arrays and a straggler set
+  const bool can_compact = m_compaction && !m_overlap && !need.aov && !m_single_launch && max_depth > m_compaction_depth;
+  auto waves_per_pass = [&](size_t groups_per_wave) {
+    const size_t n_waves = (groups_total + groups_per_wave - 1) / groups_per_wave;
+    const size_t by_index = (size_t(1) << 32) / (groups_per_wave * film.slots_per_group);  // WaveBuffers::origin is 32 bits
+    return !can_compact ? size_t(1) : std::max<size_t>(1, std::min({n_waves, (size_t)kMaxWavesPerPass, by_index}));
+  };
+  auto bytes_per_slot = [&](size_t per_pass) {
+    const size_t b = wave_bytes_per_slot(need);
+    return per_pass <= 1 ? b : b + sizeof(float4) * (per_pass - 1) + (b + sizeof(uint32_t)) / kStragglerDivisor + 1;
+  };
   if (groups_in_flight * film.slots_per_group > m_set[0].capacity + m_set[1].capacity) {
     // growing: never ask for more than the device can give (90 % of what is free plus what the waves hold now)
     size_t free_b = 0, total_b = 0;
     FR_CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
-    const size_t fit = (size_t)(0.9 * (double)(free_b + m_state_bytes)) / (wave_bytes_per_slot(need) * film.slots_per_group);
+    const size_t per_slot = bytes_per_slot(waves_per_pass(groups_in_flight));
+    const size_t fit = (size_t)(0.9 * (double)(free_b + m_state_bytes)) / (per_slot * film.slots_per_group);
     groups_in_flight = std::max<size_t>(1, std::min(groups_in_flight, fit));
+  }
+  const size_t per_pass = waves_per_pass(groups_in_flight);
+  if (per_pass >= 2) {
+    const size_t n_slots = groups_in_flight * film.slots_per_group;
+    ensure_capacity(m_set[0], n_slots, need, per_pass * n_slots);
+    ensure_capacity(m_set[1], std::max<size_t>(n_slots / kStragglerDivisor, 1024), need, 0, true);
+    WaveParams wp;
+    wp.film = film;
+    wp.n_samples = 0;
+    wp.sample_base = sample_base;
+    wp.max_depth = max_depth;
+    wp.seed = seed;
+    wp.want_aov = 0u;
+    wp.single_launch = 0u;
+    wp.camera = camera;
+    render_compacted(scene, wp, layers, n_samples, (uint32_t)(groups_in_flight << spw_log2), (uint32_t)per_pass, film_mode,
+                     class_mask);
+    return;
   }
   // two waves in flight when asked for and when the render has at least two waves' worth of samples
   const bool overlap = m_overlap && !m_time_stages && !m_single_launch && groups_in_flight >= 2 && groups_total >= 2;
@@ -323,7 +395,7 @@ void Integrator::render(const SceneView& scene, const fredholm::CameraParams& ca
   const uint32_t per_wave = (uint32_t)(groups_per_wave << spw_log2);
   const int n_sets = overlap && groups_total > groups_per_wave ? 2 : 1;
   for (int k = 0; k < n_sets; ++k) ensure_capacity(m_set[k], groups_per_wave * film.slots_per_group, need);
-  if (n_sets == 1 && m_set[1].capacity && !m_overlap) {
+  if (n_sets == 1 && m_set[1].capacity && !m_overlap && !can_compact) {
     // overlap was switched off: give the second set back
     sync_all_streams();
     m_set[1].release();
@@ -347,11 +419,7 @@ void Integrator::render(const SceneView& scene, const fredholm::CameraParams& ca
 
   cudaStream_t streams[2] = {m_stream, m_stream};
   if (n_sets == 2) {
-    if (!m_aux_stream) {
-      FR_CUDA_CHECK(cudaStreamCreateWithFlags(&m_aux_stream, cudaStreamNonBlocking));
-      FR_CUDA_CHECK(cudaEventCreateWithFlags(&m_ev_start, cudaEventDisableTiming));
-      for (auto& e : m_ev_film) FR_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    }
+    ensure_aux_stream();
     streams[1] = m_aux_stream;
     // the second stream starts after whatever the caller queued on the renderer's stream (layer clears)
     FR_CUDA_CHECK(cudaEventRecord(m_ev_start, m_stream));
@@ -380,6 +448,78 @@ void Integrator::render(const SceneView& scene, const fredholm::CameraParams& ca
   }
   // whatever follows on the renderer's stream (read-back, post-process) sees the finished layers
   if (n_sets == 2 && wave > 0 && ((wave - 1) & 1u) == 1u) FR_CUDA_CHECK(cudaStreamWaitEvent(m_stream, m_ev_film[1], 0));
+}
+
+// Wave compaction (integrator.h, set_wave_compaction): passes of up to `per_pass` waves.  m_set[0] is the wave (its
+// radiance array holds per_pass waves' worth), m_set[1] the straggler set.
+void Integrator::render_compacted(const SceneView& scene, WaveParams wp, const fredholm::RenderLayer& layers, uint32_t n_samples,
+                                  uint32_t per_wave, uint32_t per_pass, int film_mode, uint32_t class_mask)
+{
+  FR_NVTX_RANGE("render (wave compaction)");
+  ensure_aux_stream();
+  cudaStream_t s = m_stream;
+  WaveSet& wave_set = m_set[0];
+  WaveSet& late_set = m_set[1];
+  const uint32_t stride = film_groups(wp.film, per_wave) * wp.film.slots_per_group;
+  const WaveBuffers wb0 = wave_set.view();
+  WaveBuffers late = late_set.view();
+  late.origin = late_set.origin.get();
+  late.origin_stride = stride;
+  late.origin_samples = per_wave;
+  const size_t late_capacity = late_set.capacity;
+  const uint32_t depth_move = m_compaction_depth;
+  const uint32_t first_sample = wp.sample_base;
+
+  for (uint32_t done = 0; done < n_samples;) {
+    // the stragglers' sample index is relative to the first wave of the pass
+    WaveParams pass_wp = wp;
+    pass_wp.sample_base = first_sample + done;
+    WaveParams wave_wp[kMaxWavesPerPass];
+    uint32_t n_waves = 0;
+    size_t n_late = 0;
+    stage(s, STAGE_ADVANCE, [&] { launch_wave_begin(s, late, 0ull); });
+    auto finish_stragglers = [&] {
+      if (n_late == 0) return;
+      FR_NVTX_RANGE("stragglers");
+      run_bounces(s, late_set, late, pass_wp, scene, class_mask, depth_move, wp.max_depth);
+      stage(s, STAGE_ADVANCE, [&] { launch_migrate_back(s, late, (uint32_t)n_late, wave_set.L.get()); });
+      stage(s, STAGE_ADVANCE, [&] { launch_wave_begin(s, late, 0ull); });
+      n_late = 0;
+    };
+    auto wave_view = [&](uint32_t k) {
+      WaveBuffers wb = wb0;
+      wb.L = wave_set.L.get() + (size_t)k * stride;
+      return wb;
+    };
+    while (n_waves < per_pass && done < n_samples) {
+      FR_NVTX_RANGE("wave");
+      WaveParams w = wp;
+      w.n_samples = std::min(per_wave, n_samples - done);
+      w.sample_base = first_sample + done;
+      const WaveBuffers wb = wave_view(n_waves);
+      start_wave(s, wb, w);
+      // how many paths go on is known after the last shade launch: the host reads it on the second stream while
+      // that bounce's visibility rays are still being traced, so the GPU does not wait for the decision below
+      run_bounces(s, wave_set, wb, w, scene, class_mask, 0, depth_move, true);
+      FR_CUDA_CHECK(cudaEventSynchronize(m_ev_alive));
+      const uint32_t alive = *m_alive_host;
+      if (alive > late_capacity) {
+        // a scene that keeps its paths (an interior): this wave finishes where it is
+        run_bounces(s, wave_set, wb, w, scene, class_mask, depth_move, wp.max_depth);
+      } else if (alive > 0) {
+        if (n_late + alive > late_capacity) finish_stragglers();
+        stage(s, STAGE_ADVANCE, [&] { launch_migrate(s, wb, late, depth_move, n_waves * stride); });
+        m_launches++;
+        n_late += alive;
+      }
+      wave_wp[n_waves++] = w;
+      done += w.n_samples;
+    }
+    finish_stragglers();
+    // the film applies the waves in sample order (streaming mean)
+    for (uint32_t k = 0; k < n_waves; ++k)
+      stage(s, STAGE_FILM, [&] { launch_film(s, wave_wp[k], wave_view(k), layers, film_mode); });
+  }
 }
 
 void Integrator::scale_layers(const fredholm::RenderLayer& layers, uint32_t n_pixels, float scale)

@@ -84,6 +84,27 @@ class Integrator
   void set_wave_overlap(bool on) { m_overlap = on; }
   bool wave_overlap() const { return m_overlap; }
 
+  // Wave compaction (on by default).  A render of several waves pays the late bounces of every wave -- launches
+  // that carry a few per cent of the paths and run at the latency of one ray, ~3.7 ms per wave of the bench frame.
+  // With compaction a wave runs its first `depth` bounces, then the paths it still has alive move to a dense
+  // straggler set (4 float4 per path) and the wave's slots are free for the next samples; the stragglers of up to
+  // kMaxWavesPerPass waves finish their remaining bounces together, their radiance goes back to the slot it came
+  // from and the film applies the waves in sample order as before.  Every sample's arithmetic is unchanged, the
+  // image is bit-identical to the uncompacted render.  The host waits once per wave for the number of paths that
+  // go on (read on a second stream under that bounce's visibility launches, the GPU does not idle); a wave that
+  // keeps more than the straggler set holds finishes in place.
+  // Not used with first-hit AOV layers, in single-launch mode, with wave overlap, or for a one-wave render.
+  void set_wave_compaction(bool on, uint32_t depth = kDefaultCompactionDepth)
+  {
+    m_compaction = on;
+    m_compaction_depth = depth < 1u ? 1u : depth;
+  }
+  bool wave_compaction() const { return m_compaction; }
+  static constexpr uint32_t kDefaultCompactionDepth = 3;
+  static constexpr uint32_t kMaxWavesPerPass = 8;
+  // straggler slots per wave slot (1/4: the bench scene keeps 5 % of its paths after three bounces)
+  static constexpr size_t kStragglerDivisor = 4;
+
   // per-stage device time (CUDA events around every launch, on the launching stream)
   void set_stage_timing(bool on) { m_time_stages = on; }
   StageTimes stage_times();  // synchronises, returns and clears the accumulated times
@@ -115,20 +136,26 @@ class Integrator
     DevBuf<LightRay> light;
     DevBuf<WaveControl> ctl;
     DevBuf<uint32_t> sort_keys, sort_out, sort_bins;
-    size_t capacity = 0;  // path slots of the core set; 0 while the set is not valid
+    DevBuf<uint32_t> origin;  // straggler set only (WaveBuffers::origin)
+    size_t capacity = 0;    // path slots of the core set; 0 while the set is not valid
+    size_t L_capacity = 0;  // slots of the radiance array: with wave compaction it holds several waves' worth
 
-    void grow_core(size_t n_slots);
+    void grow_core(size_t n_slots, size_t l_slots);
     void release();
     size_t bytes() const;
     WaveBuffers view() const;
   };
-  void ensure_capacity(WaveSet& set, size_t n_slots, const WaveNeeds& need);
+  // l_slots (>= n_slots): size of the radiance array; with_origin: the set is a straggler set
+  void ensure_capacity(WaveSet& set, size_t n_slots, const WaveNeeds& need, size_t l_slots = 0, bool with_origin = false);
   void sync_all_streams();
 
   cudaStream_t m_stream;
   cudaStream_t m_aux_stream = nullptr;            // second wave in flight (created on first use)
-  cudaEvent_t m_ev_start = nullptr, m_ev_film[2] = {nullptr, nullptr};
+  cudaEvent_t m_ev_start = nullptr, m_ev_film[2] = {nullptr, nullptr}, m_ev_alive = nullptr;
+  uint32_t* m_alive_host = nullptr;  // pinned
   bool m_overlap = false;
+  bool m_compaction = true;
+  uint32_t m_compaction_depth = kDefaultCompactionDepth;
   size_t m_max_wave_paths = size_t(1) << 26;  // 64 Mi paths in flight (17.6 GB of wave state for a beauty-only frame)
   uint32_t m_spw_log2 = 0;
   size_t m_state_bytes = 0;
@@ -154,6 +181,15 @@ class Integrator
   const uint32_t* sorted(cudaStream_t s, WaveSet& set, const SceneView& scene, const WaveBuffers& wb, int which, bool use_octant);
   void render_wave(cudaStream_t s, WaveSet& set, const WaveBuffers& wb, const WaveParams& wp, const SceneView& scene,
                    uint32_t class_mask);
+  void start_wave(cudaStream_t s, const WaveBuffers& wb, const WaveParams& wp);
+  // probe_alive: after the shade launches of the last bounce of the range, the number of paths that go on
+  // (WaveControl::n[Q_NEXT]) is copied to m_alive_host on the second stream, under the visibility launches that
+  // follow on `s`; wait for m_ev_alive before reading it
+  void run_bounces(cudaStream_t s, WaveSet& set, const WaveBuffers& wb, const WaveParams& wp, const SceneView& scene,
+                   uint32_t class_mask, uint32_t depth_begin, uint32_t depth_end, bool probe_alive = false);
+  void ensure_aux_stream();
+  void render_compacted(const SceneView& scene, WaveParams wp, const fredholm::RenderLayer& layers, uint32_t n_samples,
+                        uint32_t per_wave, uint32_t per_pass, int film_mode, uint32_t class_mask);
 };
 
 }  // namespace frd

@@ -662,6 +662,7 @@ void Renderer::scale_layers(const RenderLayer& render_layer, float scale)
 void Renderer::set_max_wave_paths(size_t n_paths) { m_impl->integrator->set_max_wave_paths(n_paths); }
 size_t Renderer::get_wave_state_bytes() const { return m_impl->integrator->state_bytes(); }
 void Renderer::set_wave_overlap(bool on) { m_impl->integrator->set_wave_overlap(on); }
+void Renderer::set_wave_compaction(bool on, uint32_t depth) { m_impl->integrator->set_wave_compaction(on, depth); }
 void Renderer::set_single_launch(bool on) { m_impl->integrator->set_single_launch(on); }
 void Renderer::set_samples_per_warp(uint32_t spw) { m_impl->integrator->set_samples_per_warp(spw); }
 void Renderer::set_traversal_counting(bool on) { frd::set_traversal_counting(on); }

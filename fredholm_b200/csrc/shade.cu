@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(kBlock, FRD_SHADE_BLOCKS) k_shade(WaveParams w
       throughput = f3(thr4);
       const uint32_t face = __float_as_uint(hit.w);
       uint32_t px, py, sample;
-      slot_to_pixel(wp.film, slot, px, py, sample);
+      path_identity(wp.film, wb, slot, px, py, sample);
       smp = restore_sampler(wp, sample, px, py, thr4.w);
 
       // ---- surface (fill_surface_info, pt.cu:141-179) ----
@@ -440,6 +440,41 @@ __global__ void k_advance(WaveControl* ctl)
     for (int i = 0; i < 8; ++i) ctl->cursor[i] = 0;
     for (int i = 0; i < CLS_COUNT; ++i) ctl->n_class[i] = ctl->cursor_class[i] = 0;
   }
+}
+
+// ---- wave compaction (integrator.cpp): the paths a wave still has alive move to the straggler set ---------
+// Everything a path carries from one bounce to the next is its next ray, its throughput (with the sampler's
+// draw counters in .w) and its radiance so far.
+__global__ void __launch_bounds__(256) k_migrate(WaveBuffers src, WaveBuffers dst, uint32_t parity, uint32_t origin_base)
+{
+  const uint32_t n = src.ctl->n[Q_CUR];
+  const uint32_t base = dst.ctl->n[Q_CUR];  // not written by this kernel (k_migrate_commit)
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t slot = src.queue[parity][i];
+    const uint32_t j = base + i;
+    dst.ray_o[j] = src.ray_o[slot];
+    dst.ray_d[j] = src.ray_d[slot];
+    dst.thr[j] = src.thr[slot];
+    dst.L[j] = src.L[slot];
+    dst.origin[j] = origin_base + slot;
+    dst.queue[parity][j] = j;
+  }
+}
+
+__global__ void k_migrate_commit(WaveControl* src, WaveControl* dst)
+{
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    dst->n[Q_CUR] += src->n[Q_CUR];
+    src->n[Q_CUR] = 0;
+  }
+}
+
+// the stragglers' finished radiance goes back to the slot of the wave they came from (L_all = the waves' radiance
+// arrays, one after the other)
+__global__ void __launch_bounds__(256) k_migrate_back(WaveBuffers late, uint32_t n, float4* __restrict__ L_all)
+{
+  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < n) L_all[late.origin[j]] = late.L[j];
 }
 
 __global__ void k_wave_begin(WaveControl* ctl, unsigned long long n_paths)
@@ -669,6 +704,23 @@ __global__ void k_test_primary_rays(WaveParams wp, float* out)
 void launch_wave_begin(cudaStream_t s, const WaveBuffers& wb, unsigned long long n_paths)
 {
   k_wave_begin<<<1, 32, 0, s>>>(wb.ctl, n_paths);
+  FR_CUDA_LAUNCH_CHECK();
+}
+
+void launch_migrate(cudaStream_t s, const WaveBuffers& src, const WaveBuffers& dst, uint32_t depth, uint32_t origin_base)
+{
+  static GridCache cache;
+  const int grid = cache.get(reinterpret_cast<const void*>(k_migrate), 256);
+  k_migrate<<<grid, 256, 0, s>>>(src, dst, depth & 1u, origin_base);
+  FR_CUDA_LAUNCH_CHECK();
+  k_migrate_commit<<<1, 32, 0, s>>>(src.ctl, dst.ctl);
+  FR_CUDA_LAUNCH_CHECK();
+}
+
+void launch_migrate_back(cudaStream_t s, const WaveBuffers& late, uint32_t n, float4* L_all)
+{
+  if (n == 0) return;
+  k_migrate_back<<<(n + 255) / 256, 256, 0, s>>>(late, n, L_all);
   FR_CUDA_LAUNCH_CHECK();
 }
 

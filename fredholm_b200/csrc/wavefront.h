@@ -125,7 +125,15 @@ struct WaveBuffers {
   float4* pix_aov0;     // [n_pixels] that sample's first-hit words (position|depth, normal|u, albedo|v)
   float4* pix_aov1;
   float4* pix_aov2;
+  // Straggler set (integrator.cpp, wave compaction): its slots are handed out densely to the paths that several
+  // waves still had alive after a few bounces, so a slot no longer says which pixel / sample it is.  origin[slot] =
+  // wave index * origin_stride + the slot the path had in its own wave; that wave started origin_samples samples
+  // per wave index after the first one.  nullptr in an ordinary wave.
+  uint32_t* origin;
+  uint32_t origin_stride;
+  uint32_t origin_samples;
 };
+
 
 // image <-> path slot mapping.  A warp owns 32 consecutive path slots = a small pixel block times
 // `spw` consecutive samples of it (spw = 2^spw_log2 samples per warp, block = 32 / spw pixels):
@@ -194,6 +202,21 @@ struct SortGrid {
   uint32_t use_octant;  // append the direction octant to the key
 };
 __host__ __device__ inline uint32_t sort_bins(const SortGrid& g) { return 1u << (3u * g.cell_bits + (g.use_octant ? 3u : 0u)); }
+
+// which pixel and sample (relative to WaveParams::sample_base) a path slot of `wb` belongs to
+__host__ __device__ inline void path_identity(const FilmGeom& g, const WaveBuffers& wb, uint32_t slot, uint32_t& x, uint32_t& y,
+                                     uint32_t& sample)
+{
+  uint32_t first = 0;
+  if (wb.origin) {
+    const uint32_t o = wb.origin[slot];
+    const uint32_t wave = o / wb.origin_stride;
+    slot = o - wave * wb.origin_stride;
+    first = wave * wb.origin_samples;
+  }
+  slot_to_pixel(g, slot, x, y, sample);
+  sample += first;
+}
 
 struct WaveParams {
   FilmGeom film;

@@ -20,6 +20,11 @@ void launch_shade(cudaStream_t s, const WaveParams& wp, const SceneView& sc, con
 void launch_miss(cudaStream_t s, const WaveParams& wp, const SceneView& sc, const WaveBuffers& wb);
 void launch_first_hit(cudaStream_t s, const WaveParams& wp, const WaveBuffers& wb);
 void launch_advance(cudaStream_t s, const WaveBuffers& wb);
+// wave compaction: move the live paths of `src` (about to trace bounce `depth`) to the end of the straggler set
+// `dst` (two launches); origin_base = index of the wave * dst.origin_stride.  The caller has checked the capacity.
+void launch_migrate(cudaStream_t s, const WaveBuffers& src, const WaveBuffers& dst, uint32_t depth, uint32_t origin_base);
+// radiance of the first n straggler slots back into the waves' radiance arrays
+void launch_migrate_back(cudaStream_t s, const WaveBuffers& late, uint32_t n, float4* L_all);
 void launch_film(cudaStream_t s, const WaveParams& wp, const WaveBuffers& wb, const fredholm::RenderLayer& layers,
                  int film_mode);
 void launch_scale_layers(cudaStream_t s, const fredholm::RenderLayer& layers, uint32_t n_pixels, float scale);

@@ -136,6 +136,9 @@ int fr_set_film_mode(fr_renderer* r, int mode);
 int fr_set_max_wave_paths(fr_renderer* r, uint64_t n_paths);
 /* two waves in flight on two streams: fr_set_max_wave_paths is then the total of both (extension) */
 int fr_set_wave_overlap(fr_renderer* r, int on);
+/* wave compaction (extension, on by default): the paths a wave still has alive after `depth` bounces (0 = default,
+   3) move to a dense straggler set shared by up to eight waves; images are bit-identical either way */
+int fr_set_wave_compaction(fr_renderer* r, int on, uint32_t depth);
 /* device memory held for path state + ray queues (268 B / path for a beauty-only render with sun + sky) */
 uint64_t fr_get_wave_state_bytes(fr_renderer* r);
 /* 1: fr_render(n_samples) reproduces ONE reference launch of n_samples, where RadiancePayload is declared

@@ -114,6 +114,31 @@ def test_two_waves_in_flight_give_the_same_image(big):
     assert st["paths"] > 0
 
 
+def test_wave_compaction_gives_the_same_image(big):
+    """set_wave_compaction: the paths a wave still has alive after `depth` bounces finish in a straggler set shared
+    by up to eight waves.  Bit-identical to one big wave whatever the depth -- depth 1 leaves more paths alive than
+    the straggler set holds (the waves finish in place), depth 2 fills it every other wave (drained in mid-pass),
+    ten waves need two passes -- and the ray counts agree."""
+    _, r, cam = big
+    r.reset_statistics()
+    whole = render(r, cam, 10, wave=1 << 26)["beauty"]
+    st0 = r.statistics()
+    one_sample = 1 << 21
+    for on, depth in ((False, 0), (True, 1), (True, 2), (True, 3), (True, 6)):
+        r.set_wave_compaction(on, depth)
+        r.reset_statistics()
+        img = render(r, cam, 10, wave=one_sample)["beauty"]
+        st = r.statistics()
+        assert np.array_equal(img, whole), (on, depth)
+        for k in ("paths", "rays_radiance", "rays_shadow", "rays_light", "rays_skipped"):
+            assert st[k] == st0[k], (on, depth, k)
+    r.set_wave_compaction(True)
+    # sum mode at a sample offset (a multi-GPU slice), waves of two samples
+    a = render(r, cam, 6, first=5, mode="sum", wave=1 << 26)["beauty"]
+    b = render(r, cam, 6, first=5, mode="sum", wave=1 << 22)["beauty"]
+    assert np.array_equal(a, b)
+
+
 def test_sample_slices_sum_to_whole(big):
     """Multi-GPU decomposition on one GPU: slices rendered in SUM mode at their sample offset,
     added and divided, equal the single render (fp32 summation order only)."""
