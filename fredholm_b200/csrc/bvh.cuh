@@ -16,6 +16,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <cstddef>
 #include <cstdint>
 
 #include "vecmath.cuh"
@@ -23,8 +24,12 @@
 namespace frd
 {
 
-// 80-byte node, read as five 16-byte words.
-struct alignas(16) Node8 {
+// 80-byte node in a 96-byte, 32-byte-aligned record: the traversal reads it as two 256-bit words (LDG.E.256, new
+// on sm_100) and one 128-bit word -- three load instructions per node visit instead of five.  The traversal
+// kernels keep the L1 at 40-56 % of its peak throughput with every lane on a different node
+// (profiles/r2_kernels_ncu_full.txt), and for such loads the tag stage works per instruction and line, so fewer,
+// wider loads pay: +1.1 % on the bench frame (profiles/r2l_node_loads.txt) for 20 % more node bytes.
+struct alignas(32) Node8 {
   float px, py, pz;          // quantisation origin (node box lower corner)
   uint8_t ex, ey, ez;        // biased exponents of the per-axis grid step
   uint8_t imask;             // bit s set: slot s holds an internal child
@@ -34,8 +39,18 @@ struct alignas(16) Node8 {
   uint8_t qlox[8], qloy[8];  // quantised child boxes
   uint8_t qloz[8], qhix[8];
   uint8_t qhiy[8], qhiz[8];
+  uint32_t pad_[4];          // alignment only
 };
-static_assert(sizeof(Node8) == 80, "CWBVH node must be 80 bytes");
+static_assert(sizeof(Node8) == 96 && offsetof(Node8, pad_) == 80, "CWBVH node: 80 bytes of payload in a 96-byte record");
+constexpr uint32_t kNodeWords = sizeof(Node8) / 16;  // float4 words per node
+
+// 256-bit read-only load (sm_100: LDG.E.256); p must be 32-byte aligned
+__device__ __forceinline__ void ldg256(const float4* p, float4& a, float4& b)
+{
+  asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+               : "l"(p));
+}
 
 // 48-byte leaf triangle: world-space vertices; v0.w = global face index (bits),
 // v1.w = flags (bit 0: alpha-tested material, needs the any-hit path).
@@ -53,7 +68,7 @@ struct InstanceRecord {
 };
 
 struct BvhView {
-  const float4* nodes;  // Node8 as float4[5]
+  const float4* nodes;  // Node8 as float4[kNodeWords]
   const float4* tris;   // LeafTri as float4[3]
   const InstanceRecord* instances;  // two-level mode only
   const float4* w2o;                // world-to-object rows, 3 float4 per instance (two-level mode only)
@@ -309,9 +324,11 @@ struct Traverser {
     ngroup.y &= ~(1u << bit);  // what is left of this group (pushed below if the child has inner hits)
     const uint32_t slot = (bit ^ octinv) & 7u;
     const uint32_t rel = __popc(hits_imask & ~(0xffffffffu << slot));
-    const float4* np = bvh.nodes + 5ull * (ngroup.x + rel);
-    const float4 n0 = __ldg(np + 0), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3),
-                 n4 = __ldg(np + 4);
+    const float4* np = bvh.nodes + (unsigned long long)kNodeWords * (ngroup.x + rel);
+    float4 n0, n1, n2, n3;
+    ldg256(np, n0, n1);
+    ldg256(np + 2, n2, n3);
+    const float4 n4 = __ldg(np + 4);
     if (COUNT) cnt->nodes++;
     const uint32_t ew = __float_as_uint(n0.w);
     const float sx = __uint_as_float((ew & 0xffu) << 23);

@@ -605,6 +605,7 @@ __device__ void collapse_node(uint32_t n8, uint32_t* __restrict__ work, int n, c
   const uint32_t tbase = n_leaf_tris ? atomicAdd(&counters->n_tris, n_leaf_tris) : 0u;
 
   Node8 out;
+  out.pad_[0] = out.pad_[1] = out.pad_[2] = out.pad_[3] = 0u;
   out.px = nlo.x;
   out.py = nlo.y;
   out.pz = nlo.z;

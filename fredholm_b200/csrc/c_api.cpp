@@ -334,13 +334,14 @@ int fr_get_accel_data(fr_renderer* r, void* nodes80, void* tris48)
       // two-level structure: the combined arrays -- n_nodes nodes, (instances + stored faces) 48-byte records
       const frd::TwoLevelBvh& t = r->renderer.impl()->bvh2;
       FR_CUDA_CHECK(cudaDeviceSynchronize());
-      if (nodes80) FR_CUDA_CHECK(cudaMemcpy(nodes80, t.nodes.get(), sizeof(frd::Node8) * t.n_nodes, cudaMemcpyDeviceToHost));
+      if (nodes80) FR_CUDA_CHECK(cudaMemcpy2D(nodes80, 80, t.nodes.get(), sizeof(frd::Node8), 80, t.n_nodes, cudaMemcpyDeviceToHost));
       if (tris48) FR_CUDA_CHECK(cudaMemcpy(tris48, t.tris.get(), 48ull * (t.n_instances + t.n_blas_faces), cudaMemcpyDeviceToHost));
       return;
     }
     const frd::DeviceBvh& b = r->renderer.impl()->bvh;
     FR_CUDA_CHECK(cudaDeviceSynchronize());
-    if (nodes80) FR_CUDA_CHECK(cudaMemcpy(nodes80, b.nodes.get(), sizeof(frd::Node8) * b.n_nodes, cudaMemcpyDeviceToHost));
+    // 80 bytes per node whatever the stride of the device array (Node8 may carry alignment padding)
+    if (nodes80) FR_CUDA_CHECK(cudaMemcpy2D(nodes80, 80, b.nodes.get(), sizeof(frd::Node8), 80, b.n_nodes, cudaMemcpyDeviceToHost));
     if (tris48) FR_CUDA_CHECK(cudaMemcpy(tris48, b.tris.get(), 48ull * b.n_faces, cudaMemcpyDeviceToHost));
   });
 }

@@ -17,6 +17,15 @@ WANT = [
     ("smsp__inst_executed.sum", "warp instructions"),
     ("l1tex__t_sector_hit_rate.pct", "L1 hit %"),
     ("lts__t_sector_hit_rate.pct", "L2 hit %"),
+    ("l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "L1/TEX throughput %"),
+    ("l1tex__lsu_writeback_active.avg.pct_of_peak_sustained_elapsed", "L1 LSU writeback busy %"),
+    ("l1tex__data_pipe_lsu_wavefronts.sum", "L1 LSU data-stage wavefronts"),
+    ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "  of which shared memory"),
+    ("l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum", "global load requests (warp level)"),
+    ("l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum", "global load sectors"),
+    ("lts__throughput.avg.pct_of_peak_sustained_elapsed", "L2 throughput %"),
+    ("sm__inst_executed_pipe_lsu.sum", "LSU pipe warp instructions"),
+    ("sm__inst_executed_pipe_xu.sum", "XU pipe warp instructions"),
     ("dram__bytes_read.sum", "DRAM read"),
     ("dram__bytes_write.sum", "DRAM write"),
     ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "DRAM throughput %"),
