@@ -366,6 +366,7 @@ def run_ours(args):
     stats = r.statistics()
     stages = r.stage_times()
     r.set_stage_timing(False)
+    wave_state_bytes = r.wave_state_bytes()   # of the timed frames (the 4096-sample sub-record below holds more)
     total_ms = max_over_ranks(float(sum(step_ms)))
     if world > 1:
         cnt = torch.tensor([stats["paths"], stats["rays"], stats["kernel_launches"], stats["rays_skipped"]],
@@ -495,9 +496,10 @@ def run_ours(args):
         "config": {"workload": workload_name(args, scene), "samples_per_gpu": spp, "parallelism": "sample-sharded x%d" % world,
                    "collective": None if world == 1 else "one ncclReduce of the beauty sums per frame, issued by the C++ core (fr_render_sharded)",
                    "wave_paths": wave_paths(args),
-                   "wave_state_gb": round(r.wave_state_bytes() / 1e9, 2),
+                   "wave_state_gb": round(wave_state_bytes / 1e9, 2),
+                   "wave_compaction": "waves of %d samples; the paths alive after 3 bounces finish in a straggler set shared by the frame's waves" % WAVE_SPP,
                    "l2": "per-step working set (path state + queues, %.1f GB) exceeds the 126 MB L2; no explicit flush"
-                         % (r.wave_state_bytes() / 1e9),
+                         % (wave_state_bytes / 1e9),
                    "bvh": {"nodes": accel["n_nodes"], "depth": accel["depth"], "build_ms": round(accel["build_ms"], 2),
                            "bytes": accel["bytes"]}},
         "mrays_per_s": rays_all / secs / 1e6,
