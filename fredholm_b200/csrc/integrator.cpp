@@ -353,7 +353,7 @@ void Integrator::render(const SceneView& scene, const fredholm::CameraParams& ca
   const size_t groups_total = film_groups(film, n_samples);
   size_t groups_in_flight = std::max<size_t>(1, std::min<size_t>(groups_total, m_max_wave_paths / film.slots_per_group));
   // wave compaction: a pass of up to kMaxWavesPerPass waves keeps all their radiance arrays and a straggler set
-  const bool can_compact = m_compaction && !m_overlap && !need.aov && !m_single_launch && max_depth > m_compaction_depth;
+  const bool can_compact = m_compaction && !m_overlap && !m_single_launch && max_depth > m_compaction_depth;
   auto waves_per_pass = [&](size_t groups_per_wave) {
     const size_t n_waves = (groups_total + groups_per_wave - 1) / groups_per_wave;
     const size_t by_index = (size_t(1) << 32) / (groups_per_wave * film.slots_per_group);  // WaveBuffers::origin is 32 bits
@@ -361,7 +361,10 @@ void Integrator::render(const SceneView& scene, const fredholm::CameraParams& ca
   };
   auto bytes_per_slot = [&](size_t per_pass) {
     const size_t b = wave_bytes_per_slot(need);
-    return per_pass <= 1 ? b : b + sizeof(float4) * (per_pass - 1) + (b + sizeof(uint32_t)) / kStragglerDivisor + 1;
+    WaveNeeds late_need = need;
+    late_need.aov = false;
+    const size_t late = wave_bytes_per_slot(late_need) + sizeof(uint32_t);
+    return per_pass <= 1 ? b : b + sizeof(float4) * (per_pass - 1) + late / kStragglerDivisor + 1;
   };
   if (groups_in_flight * film.slots_per_group > m_set[0].capacity + m_set[1].capacity) {
     // growing: never ask for more than the device can give (90 % of what is free plus what the waves hold now)
@@ -375,14 +378,16 @@ void Integrator::render(const SceneView& scene, const fredholm::CameraParams& ca
   if (per_pass >= 2) {
     const size_t n_slots = groups_in_flight * film.slots_per_group;
     ensure_capacity(m_set[0], n_slots, need, per_pass * n_slots);
-    ensure_capacity(m_set[1], std::max<size_t>(n_slots / kStragglerDivisor, 1024), need, 0, true);
+    WaveNeeds late_need = need;
+    late_need.aov = false;  // the first-hit words are complete after the first bounce and stay with the wave
+    ensure_capacity(m_set[1], std::max<size_t>(n_slots / kStragglerDivisor, 1024), late_need, 0, true);
     WaveParams wp;
     wp.film = film;
     wp.n_samples = 0;
     wp.sample_base = sample_base;
     wp.max_depth = max_depth;
     wp.seed = seed;
-    wp.want_aov = 0u;
+    wp.want_aov = need.aov ? 1u : 0u;
     wp.single_launch = 0u;
     wp.camera = camera;
     render_compacted(scene, wp, layers, n_samples, (uint32_t)(groups_in_flight << spw_log2), (uint32_t)per_pass, film_mode,
@@ -469,6 +474,9 @@ void Integrator::render_compacted(const SceneView& scene, WaveParams wp, const f
   const size_t late_capacity = late_set.capacity;
   const uint32_t depth_move = m_compaction_depth;
   const uint32_t first_sample = wp.sample_base;
+  fredholm::RenderLayer first_hit_layers = layers, beauty_layer = {};
+  first_hit_layers.beauty = nullptr;
+  beauty_layer.beauty = layers.beauty;
 
   for (uint32_t done = 0; done < n_samples;) {
     // the stragglers' sample index is relative to the first wave of the pass
@@ -512,13 +520,19 @@ void Integrator::render_compacted(const SceneView& scene, WaveParams wp, const f
         m_launches++;
         n_late += alive;
       }
+      // the first-hit layers are complete after the first bounce and the wave's slots are about to be reused:
+      // they go to the film now (in sample order, as every wave does this), the beauty layer at the end of the pass
+      if (w.want_aov) stage(s, STAGE_FILM, [&] { launch_film(s, w, wb, first_hit_layers, film_mode); });
       wave_wp[n_waves++] = w;
       done += w.n_samples;
     }
     finish_stragglers();
     // the film applies the waves in sample order (streaming mean)
-    for (uint32_t k = 0; k < n_waves; ++k)
-      stage(s, STAGE_FILM, [&] { launch_film(s, wave_wp[k], wave_view(k), layers, film_mode); });
+    for (uint32_t k = 0; k < n_waves; ++k) {
+      WaveParams w = wave_wp[k];
+      w.want_aov = 0u;
+      stage(s, STAGE_FILM, [&] { launch_film(s, w, wave_view(k), beauty_layer, film_mode); });
+    }
   }
 }
 

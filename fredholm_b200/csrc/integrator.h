@@ -93,7 +93,8 @@ class Integrator
   // image is bit-identical to the uncompacted render.  The host waits once per wave for the number of paths that
   // go on (read on a second stream under that bounce's visibility launches, the GPU does not idle); a wave that
   // keeps more than the straggler set holds finishes in place.
-  // Not used with first-hit AOV layers, in single-launch mode, with wave overlap, or for a one-wave render.
+  // With first-hit AOV layers bound, those go to the film when their wave has finished its first bounces and the
+  // beauty layer at the end of the pass.  Not used in single-launch mode, with wave overlap, or for a one-wave render.
   void set_wave_compaction(bool on, uint32_t depth = kDefaultCompactionDepth)
   {
     m_compaction = on;

@@ -513,7 +513,8 @@ __global__ void __launch_bounds__(256) k_film(WaveParams wp, WaveBuffers wb, fre
   if (x >= wp.film.width || y >= wp.film.height) return;
   const uint32_t pixel = x + wp.film.width * y;
 
-  float3 beauty = f3(layers.beauty[pixel]);
+  // (wave compaction applies the first-hit layers and the beauty layer in two passes: either may be unbound)
+  float3 beauty = layers.beauty ? f3(layers.beauty[pixel]) : f3(0.f);
   float3 position = layers.position ? f3(layers.position[pixel]) : f3(0.f);
   float3 normal = layers.normal ? f3(layers.normal[pixel]) : f3(0.f);
   float depth = layers.depth ? layers.depth[pixel] : 0.f;
@@ -527,8 +528,7 @@ __global__ void __launch_bounds__(256) k_film(WaveParams wp, WaveBuffers wb, fre
   uint32_t n_spp = wp.sample_base;
   for (uint32_t s = 0; s < wp.n_samples; ++s) {
     const uint32_t slot = pixel_to_slot(wp.film, x, y, s);
-    const float4 L = wb.L[slot];
-    float3 radiance = f3(L);
+    float3 radiance = layers.beauty ? f3(wb.L[slot]) : f3(0.f);
     if (bad3(radiance)) radiance = f3(0.f);  // pt.cu:475-478
     float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0;
     if (wp.single_launch) {
@@ -556,7 +556,7 @@ __global__ void __launch_bounds__(256) k_film(WaveParams wp, WaveBuffers wb, fre
     }
     n_spp++;
   }
-  layers.beauty[pixel] = make_float4(beauty.x, beauty.y, beauty.z, 1.0f);
+  if (layers.beauty) layers.beauty[pixel] = make_float4(beauty.x, beauty.y, beauty.z, 1.0f);
   if (layers.position) layers.position[pixel] = make_float4(position.x, position.y, position.z, 1.0f);
   if (layers.normal) layers.normal[pixel] = make_float4(normal.x, normal.y, normal.z, 1.0f);
   if (layers.depth) layers.depth[pixel] = depth;

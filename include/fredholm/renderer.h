@@ -136,8 +136,8 @@ class Renderer
   void set_wave_overlap(bool on);
   // Wave compaction (on by default): in a render of several waves, the few paths a wave still has alive after
   // `depth` bounces move to a dense straggler set that finishes the remaining bounces of up to eight waves
-  // together, so small waves no longer pay their own nearly empty late launches.  Bit-identical images; one
-  // host synchronisation per wave.  Beauty-only renders (no first-hit AOV layers), not in single-launch mode.
+  // together, so small waves no longer pay their own nearly empty late launches.  Bit-identical layers; the host
+  // waits once per wave for a path count.  Not in single-launch mode.
   void set_wave_compaction(bool on, uint32_t depth = 3);
   // One render(n_samples) call behaves like ONE reference launch of n_samples: payload.firsthit and the
   // first-hit AOVs outlive the sample loop (pt.cu:432-433, 744-759) -- what app/rtcamp8.cpp produces.  Off by

@@ -137,6 +137,12 @@ def test_wave_compaction_gives_the_same_image(big):
     a = render(r, cam, 6, first=5, mode="sum", wave=1 << 26)["beauty"]
     b = render(r, cam, 6, first=5, mode="sum", wave=1 << 22)["beauty"]
     assert np.array_equal(a, b)
+    # with the first-hit layers bound: they go to the film wave by wave, the beauty layer at the end of the pass
+    names = ("beauty", "position", "normal", "depth", "texcoord", "albedo")
+    a = render(r, cam, 4, wave=1 << 26, names=names)
+    b = render(r, cam, 4, wave=one_sample, names=names)
+    for n in names:
+        assert np.array_equal(a[n], b[n], equal_nan=True), n
 
 
 def test_sample_slices_sum_to_whole(big):
