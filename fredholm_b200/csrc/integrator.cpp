@@ -62,7 +62,7 @@ const uint32_t* Integrator::sorted(cudaStream_t s, WaveSet& set, const SceneView
 Integrator::~Integrator()
 {
   for (auto& t : m_timed) {
-    cudaEventDestroy(t.e0);
+    if (t.owns_e0) cudaEventDestroy(t.e0);
     cudaEventDestroy(t.e1);
   }
   for (auto e : m_event_pool) cudaEventDestroy(e);
@@ -102,11 +102,14 @@ void Integrator::stage(cudaStream_t s, int id, F&& launch)
   if (!m_time_stages) {
     launch();
   } else {
-    TimedLaunch t{id, get_event(), get_event()};
-    FR_CUDA_CHECK(cudaEventRecord(t.e0, s));
+    const bool chained = m_chain_event != nullptr && m_chain_stream == s;
+    TimedLaunch t{id, chained ? m_chain_event : get_event(), get_event(), !chained};
+    if (!chained) FR_CUDA_CHECK(cudaEventRecord(t.e0, s));
     launch();
     FR_CUDA_CHECK(cudaEventRecord(t.e1, s));
     m_timed.push_back(t);
+    m_chain_event = t.e1;
+    m_chain_stream = s;
   }
   m_launches++;
 }
@@ -126,10 +129,11 @@ StageTimes Integrator::stage_times()
     FR_CUDA_CHECK(cudaEventElapsedTime(&ms, t.e0, t.e1));
     out.ms[t.stage] += ms;
     out.launches[t.stage]++;
-    m_event_pool.push_back(t.e0);
+    if (t.owns_e0) m_event_pool.push_back(t.e0);
     m_event_pool.push_back(t.e1);
   }
   m_timed.clear();
+  m_chain_event = nullptr;
   return out;
 }
 
@@ -340,6 +344,7 @@ void Integrator::render(const SceneView& scene, const fredholm::CameraParams& ca
                         uint32_t n_samples, uint32_t max_depth, uint32_t seed, int film_mode, uint32_t class_mask)
 {
   if (width == 0 || height == 0 || n_samples == 0) return;
+  m_chain_event = nullptr;  // stage timing: the caller may have queued work on the stream since the last launch
   // samples per warp: never more than the call's sample count needs (a 1-spp render keeps 8x4 tiles)
   uint32_t spw_log2 = m_spw_log2;
   while (spw_log2 > 0 && (1u << spw_log2) > n_samples) spw_log2--;

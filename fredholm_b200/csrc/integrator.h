@@ -162,10 +162,15 @@ class Integrator
   size_t m_state_bytes = 0;
   unsigned long long m_launches = 0;
 
+  // Stage timing: consecutive launches on one stream share an event (the end of one is the start of the next), so
+  // a timed frame records one event per launch, not two.
   struct TimedLaunch {
     int stage;
     cudaEvent_t e0, e1;
+    bool owns_e0;
   };
+  cudaEvent_t m_chain_event = nullptr;  // end of the last timed launch ...
+  cudaStream_t m_chain_stream = nullptr;  // ... on this stream; reset whenever other work may have been queued
   bool m_time_stages = false;
   std::vector<TimedLaunch> m_timed;
   std::vector<cudaEvent_t> m_event_pool;
