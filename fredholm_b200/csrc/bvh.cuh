@@ -126,9 +126,14 @@ FR_D float shear_dot(float ax, float ay, float az, const float c[3])
 }
 
 // true if tmin < t < tlim (or t == tlim when allow_equal), outputs t,u,v
+// OCCLUSION = true (any-hit rays): only WHETHER the triangle is hit inside (tmin, tlim) matters, so the division
+// is replaced by comparing the scaled distance T against tmin |det| and tlim |det| (same edge functions, same
+// sign rules; the outcome can differ from the divided form only for a distance within an ulp of an end of the
+// interval).  t, bu, bv are then only computed when want_uv is set (alpha-tested triangles).
+template <bool OCCLUSION>
 FR_D bool watertight_hit(const RayShear& s, const float3& o, const float4& v0, const float4& v1,
                          const float4& v2, float tmin, float tlim, bool allow_equal, float& t,
-                         float& bu, float& bv)
+                         float& bu, float& bv, bool want_uv = true)
 {
   const float Ax0 = __fsub_rn(v0.x, o.x), Ay0 = __fsub_rn(v0.y, o.y), Az0 = __fsub_rn(v0.z, o.z);
   const float Bx0 = __fsub_rn(v1.x, o.x), By0 = __fsub_rn(v1.y, o.y), Bz0 = __fsub_rn(v1.z, o.z);
@@ -151,7 +156,13 @@ FR_D bool watertight_hit(const RayShear& s, const float3& o, const float4& v0, c
   const float Bz = shear_dot(Bx0, By0, Bz0, s.cz);
   const float Cz = shear_dot(Cx0, Cy0, Cz0, s.cz);
   const float T = __fmaf_rn(W, Cz, __fmaf_rn(V, Bz, __fmul_rn(U, Az)));
-  const float rcp = __fdiv_rn(1.0f, det);
+  if (OCCLUSION) {
+    const float ad = fabsf(det);
+    const float Ts = __uint_as_float(__float_as_uint(T) ^ (__float_as_uint(det) & 0x80000000u));
+    if (!(Ts > tmin * ad) || !(Ts < tlim * ad)) return false;
+    if (!want_uv) return true;
+  }
+  const float rcp = __frcp_rn(det);  // the correctly rounded 1 / det, as the host oracle's 1.0f / det (shorter than __fdiv_rn)
   const float tt = __fmul_rn(T, rcp);
   if (!(tt > tmin)) return false;
   if (!(tt < tlim || (allow_equal && tt == tlim))) return false;
@@ -430,11 +441,12 @@ struct Traverser {
       tgroup2 = make_uint2(0u, 0u);
     }
     if (COUNT) cnt->tris++;
-    float t, u, v;
-    if (!watertight_hit(sh, o, v0, v1, v2, tmin, best.t, best.face != kNoHit, t, u, v)) return false;
+    float t = 0.0f, u = 0.0f, v = 0.0f;
+    const bool alpha_tested = (__float_as_uint(v1.w) & 1u) != 0u;
+    if (!watertight_hit<ANY>(sh, o, v0, v1, v2, tmin, best.t, best.face != kNoHit, t, u, v, alpha_tested)) return false;
     const uint32_t face = __float_as_uint(v0.w) + (TWO ? bvh.instances[inst].face_offset : 0u);
-    if (t == best.t && best.face != kNoHit && face > best.face) return false;
-    if ((__float_as_uint(v1.w) & 1u) && !anyhit(face, u, v)) return false;
+    if (!ANY && t == best.t && best.face != kNoHit && face > best.face) return false;
+    if (alpha_tested && !anyhit(face, u, v)) return false;
     best.t = t;
     best.u = u;
     best.v = v;

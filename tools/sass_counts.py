@@ -48,17 +48,25 @@ text = open(src).read().split("\n")
 # the zero-edge double fallback inside watertight_hit
 dbl = [i + 1 for i, l in enumerate(text) if "__dsub_rn" in l or "(U == 0.0f || V == 0.0f || W == 0.0f)" in l]
 DOUBLE = (min(dbl), max(dbl) + 1) if dbl else (0, -1)
+# the divided tail of watertight_hit (1 / det, t, u, v): any-hit kernels run it only for alpha-tested triangles
+rcp = [i + 1 for i, l in enumerate(text) if "const float rcp = " in l]
+UV_TAIL = (rcp[0], next(i + 1 for i in range(rcp[0], len(text)) if text[i].startswith("}"))) if rcp else (0, -1)
 
 with tempfile.TemporaryDirectory() as tmp:
     subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(obj)], cwd=tmp, check=True, capture_output=True)
     cubins = [f for f in os.listdir(tmp) if f.endswith(".cubin")]
     assert len(cubins) == 1, cubins
     cubin = os.path.join(tmp, cubins[0])
-    sha = hashlib.sha256(open(cubin, "rb").read()).hexdigest()
     dis = subprocess.run(["nvdisasm", "-g", "-c", cubin], capture_output=True, text=True, check=True).stdout
 
-result = {"cubin": os.path.basename(obj), "cubin_sha256": sha, "source": "nvdisasm -g line attribution, tools/sass_counts.py",
-          "line_ranges": {"node": NODE, "triangle": TRI, "double_fallback": DOUBLE}, "kernels": {}}
+# Identity of the build = sha256 of the traversal kernels' instruction stream (kernel names and instruction text, without
+# addresses and encodings).  NOT of the cubin file: nvcc puts a fresh unique id into the names of internal-linkage
+# symbols at every compilation, so two builds of the same source differ as files while their code is identical.
+UNIQUE = re.compile(r"_GLOBAL__N__[0-9a-f]+_\d+_[A-Za-z0-9_]+?_cu_[0-9a-f]+")
+hash_lines = []
+result = {"cubin": os.path.basename(obj), "cubin_sha256": None, "hash_of": "instruction stream of the k_trace_* kernels (names + SASS text)",
+          "source": "nvdisasm -g line attribution, tools/sass_counts.py",
+          "line_ranges": {"node": NODE, "triangle": TRI, "double_fallback": DOUBLE, "uv_tail": UV_TAIL}, "kernels": {}}
 cur, file_, line = None, None, 0
 for l in dis.split("\n"):
     m = re.match(r"\.text\.(\S+):", l)
@@ -73,7 +81,9 @@ for l in dis.split("\n"):
             counting = len(targs) == 2 and targs[0]
             two = targs[-1] if targs else False
             name = km.group(1) + ("_count" if counting else "") + ("_two_level" if two else "")
-            cur = result["kernels"].setdefault(name, {"total": 0, "c_node": 0, "c_tri": 0, "c_tri_double_fallback": 0})
+            cur = result["kernels"].setdefault(name, {"total": 0, "c_node": 0, "c_tri": 0, "c_tri_double_fallback": 0,
+                                                      "c_tri_alpha_only": 0, "any_hit": "shadow" in name})
+            hash_lines.append("== " + name)
         continue
     m = re.match(r'\s*//## File "([^"]+)", line (\d+)', l)
     if m:
@@ -82,12 +92,16 @@ for l in dis.split("\n"):
     if cur is None or not re.match(r"\s*/\*[0-9a-f]{4,}\*/", l):
         continue
     cur["total"] += 1
+    hash_lines.append(UNIQUE.sub("_anon_", re.sub(r"/\*[0-9a-f]{4,}\*/", "", l)).strip())
     if file_ == "bvh.cuh":
         if DOUBLE[0] <= line <= DOUBLE[1]:
             cur["c_tri_double_fallback"] += 1
+        elif cur["any_hit"] and UV_TAIL[0] <= line <= UV_TAIL[1]:
+            cur["c_tri_alpha_only"] += 1  # not part of c_tri: off the common path of an any-hit kernel
         elif any(a <= line <= b for a, b in TRI):
             cur["c_tri"] += 1
         elif any(a <= line <= b for a, b in NODE):
             cur["c_node"] += 1
+result["cubin_sha256"] = hashlib.sha256("\n".join(hash_lines).encode()).hexdigest()
 json.dump(result, open(out_path, "w"), indent=1)
 print(json.dumps(result["kernels"]))
