@@ -137,6 +137,14 @@ def test_wave_compaction_gives_the_same_image(big):
     a = render(r, cam, 6, first=5, mode="sum", wave=1 << 26)["beauty"]
     b = render(r, cam, 6, first=5, mode="sum", wave=1 << 22)["beauty"]
     assert np.array_equal(a, b)
+    # a last wave that is not full (7 = 2 + 2 + 2 + 1), and sample groups of four per warp (7 = 4 + 3, waves of one group)
+    a = render(r, cam, 7, wave=1 << 26)["beauty"]
+    assert np.array_equal(a, render(r, cam, 7, wave=1 << 22)["beauty"])
+    r.set_samples_per_warp(4)
+    try:
+        assert np.array_equal(a, render(r, cam, 7, wave=1 << 23)["beauty"])
+    finally:
+        r.set_samples_per_warp(1)
     # with the first-hit layers bound: they go to the film wave by wave, the beauty layer at the end of the pass
     names = ("beauty", "position", "normal", "depth", "texcoord", "albedo")
     a = render(r, cam, 4, wave=1 << 26, names=names)
